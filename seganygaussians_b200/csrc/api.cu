@@ -1,0 +1,307 @@
+// api.cu -- the C ABI (include/sagars.h): host orchestration of the forward / backward stages.
+//
+// Replaces the host side of the reference: CudaRasterizer::Rasterizer::{forward,backward,markVisible}
+// (CF cuda_rasterizer/rasterizer_impl.cu:141-153,198-434) and the scratch carving of
+// GeometryState / ImageState / BinningState (rasterizer_impl.cu:155-194).
+#include "common.cuh"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace sagars {
+
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
+{
+    const char* base = strrchr(file, '/');
+    set_error("[CUDA ERROR] %s (%s) at %s:%d", cudaGetErrorString(e), what, base ? base + 1 : file, line);
+    return SAGARS_ECUDA;
+}
+
+void count_launch(int n) { g_launches += n; }
+
+// same rule as the reference's getHigherMsb (CF rasterizer_impl.cu:35-50): bits needed for tile ids
+static uint32_t higher_msb(uint32_t n)
+{
+    uint32_t msb = sizeof(n) * 4;
+    uint32_t step = msb;
+    while (step > 1) {
+        step /= 2;
+        if (n >> msb) msb += step;
+        else msb -= step;
+    }
+    if (n >> msb) msb++;
+    return msb;
+}
+
+static int fill_dims(Dims& d, int P, int D, int M, int C, int W, int H, float tfx, float tfy, float mod)
+{
+    if (P < 0 || W <= 0 || H <= 0) {
+        set_error("bad dimensions P=%d W=%d H=%d", P, W, H);
+        return SAGARS_EINVAL;
+    }
+    if (C < 1 || C > SAGARS_MAX_CHANNELS) {
+        set_error("unsupported channel count %d (1..%d)", C, SAGARS_MAX_CHANNELS);
+        return SAGARS_EINVAL;
+    }
+    d.P = P; d.D = D; d.M = M; d.C = C; d.W = W; d.H = H;
+    d.tiles_x = (W + TILE_X - 1) / TILE_X;
+    d.tiles_y = (H + TILE_Y - 1) / TILE_Y;
+    d.tan_fovx = tfx; d.tan_fovy = tfy;
+    d.focal_y = H / (2.0f * tfy);
+    d.focal_x = W / (2.0f * tfx);
+    d.scale_modifier = mod;
+    return SAGARS_OK;
+}
+
+}  // namespace sagars
+
+using namespace sagars;
+
+extern "C" {
+
+int sagars_abi_version(void) { return SAGARS_ABI_VERSION; }
+const char* sagars_arch(void) { return "sm_100a"; }
+const char* sagars_last_error(void) { return g_err; }
+int64_t sagars_launch_count(void) { return g_launches; }
+void sagars_reset_launch_count(void) { g_launches = 0; }
+
+size_t sagars_geom_bytes(int32_t P) { return geom_layout((size_t)(P < 0 ? 0 : P)).total; }
+size_t sagars_image_bytes(int32_t W, int32_t H) { return image_layout(W, H).total; }
+size_t sagars_binning_bytes(int32_t R) { return binning_total((size_t)(R < 0 ? 0 : R)); }
+size_t sagars_grad_scratch_bytes(int32_t P) { return grad_scratch_bytes((size_t)(P < 0 ? 0 : P)); }
+size_t sagars_sort_temp_bytes(int32_t n)
+{
+    const size_t m = (size_t)(n < 0 ? 0 : n);
+    return align_up(m * 8) + align_up(m * 4) + sort_temp_bytes(m) + 256;
+}
+
+int sagars_get_geom_layout(int32_t P, sagars_geom_layout* out)
+{
+    if (!out || P < 0) { set_error("bad argument"); return SAGARS_EINVAL; }
+    *out = geom_layout((size_t)P);
+    return SAGARS_OK;
+}
+int sagars_get_image_layout(int32_t W, int32_t H, sagars_image_layout* out)
+{
+    if (!out || W <= 0 || H <= 0) { set_error("bad argument"); return SAGARS_EINVAL; }
+    *out = image_layout(W, H);
+    return SAGARS_OK;
+}
+int sagars_get_binning_layout(int32_t R, sagars_binning_layout* out)
+{
+    if (!out || R < 0) { set_error("bad argument"); return SAGARS_EINVAL; }
+    *out = binning_layout((size_t)R);
+    out->total = binning_total((size_t)R);
+    return SAGARS_OK;
+}
+
+int sagars_forward(const sagars_forward_args* a,
+                   sagars_alloc_fn geom_alloc, void* geom_user,
+                   sagars_alloc_fn binning_alloc, void* binning_user,
+                   sagars_alloc_fn image_alloc, void* image_user,
+                   int32_t* num_rendered, void* stream_)
+{
+    g_err[0] = 0;
+    if (!a || !geom_alloc || !binning_alloc || !image_alloc || !num_rendered) {
+        set_error("sagars_forward: NULL argument");
+        return SAGARS_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream_;
+    const bool debug = (a->flags & SAGARS_FLAG_DEBUG) != 0;
+    const bool mask_only = (a->flags & SAGARS_FLAG_MASK_ONLY) != 0;
+    const bool md = (a->flags & (SAGARS_FLAG_MASK_DEPTH | SAGARS_FLAG_MASK_ONLY)) != 0;
+    *num_rendered = 0;
+
+    Dims d;
+    int rc = fill_dims(d, a->P, a->D, a->M, a->num_channels, a->width, a->height, a->tan_fovx, a->tan_fovy, a->scale_modifier);
+    if (rc) return rc;
+    if (a->P == 0) return SAGARS_OK;   // nothing is launched; caller pre-zeroes outputs (CF rasterize_points.cu:81)
+    if (!a->means3D || !a->opacities || !a->viewmatrix || !a->projmatrix || !a->radii || !a->background ||
+        (!mask_only && !a->out_color)) {
+        set_error("sagars_forward: missing required pointer");
+        return SAGARS_EINVAL;
+    }
+    if (!mask_only && a->colors_precomp == nullptr) {
+        // the reference's message for the non-RGB build (CF rasterizer_impl.cu:242-245)
+        if (a->num_channels != 3) {
+            set_error("For non-RGB, provide precomputed Gaussian colors!");
+            return SAGARS_ENOCOLOR;
+        }
+        if (!a->shs || !a->cam_pos || a->M <= 0) {
+            set_error("sagars_forward: neither colors_precomp nor shs given");
+            return SAGARS_EINVAL;
+        }
+    }
+    if (a->cov3D_precomp == nullptr && (!a->scales || !a->rotations)) {
+        set_error("sagars_forward: neither cov3D_precomp nor scales/rotations given");
+        return SAGARS_EINVAL;
+    }
+    if (md && (!a->mask || !a->out_mask)) {
+        set_error("sagars_forward: mask / out_mask required for the depth variant");
+        return SAGARS_EINVAL;
+    }
+    SAGARS_CUDA(cudaSetDevice(a->device));
+
+    void* geom_mem = geom_alloc(geom_user, geom_layout(d.P).total);
+    void* img_mem = image_alloc(image_user, image_layout(d.W, d.H).total);
+    if (!geom_mem || !img_mem) { set_error("allocator callback returned NULL"); return SAGARS_EALLOC; }
+    GeomView g = geom_view(geom_mem, d.P);
+    ImageView im = image_view(img_mem, d.W, d.H);
+
+    SAGARS_CUDA(cudaMemsetAsync(g.status, 0, 64, s));
+    rc = launch_preprocess(*a, d, g, s, debug);
+    if (rc) return rc;
+    rc = launch_scan_block_sums(d, g, s, debug);
+    if (rc) return rc;
+
+    // the one host synchronisation of the forward pass: R sizes the binning buffer
+    uint32_t status_h[2] = {0, 0};
+    SAGARS_CUDA(cudaMemcpyAsync(status_h, g.status, sizeof(status_h), cudaMemcpyDeviceToHost, s));
+    SAGARS_CUDA(cudaStreamSynchronize(s));
+    if (status_h[0] != 0) {
+        set_error("Point is filtered although prefiltered is set. This shouldn't happen!");
+        return SAGARS_EPREFILTER;
+    }
+    const int R = (int)status_h[1];
+    *num_rendered = R;
+
+    void* bin_mem = binning_alloc(binning_user, binning_total((size_t)R));
+    if (!bin_mem) { set_error("allocator callback returned NULL"); return SAGARS_EALLOC; }
+    BinningView bv = binning_view(bin_mem, (size_t)R);
+
+    const int num_tiles = d.tiles_x * d.tiles_y;
+    const int end_bit = 32 + (int)higher_msb((uint32_t)num_tiles);
+    const bool use_cub = (a->flags & SAGARS_FLAG_CUB_SORT) != 0;
+    if (R > 0) {
+        // own sort: emit into the buffer from which an npass-long ping-pong ends in the final arrays
+        const bool start_alt = !use_cub && (sort_num_passes(end_bit) & 1);
+        uint64_t* k0 = start_alt ? bv.keys_alt : bv.point_list_keys;
+        uint32_t* v0 = start_alt ? bv.vals_alt : bv.point_list;
+        rc = launch_duplicate(d, g, a->radii, k0, v0, s, debug);
+        if (rc) return rc;
+        bool in_a = true;
+        rc = launch_sort_pairs(R, end_bit, bv.point_list_keys, bv.point_list, bv.keys_alt, bv.vals_alt, bv.sort_temp,
+                               sort_temp_bytes((size_t)R), use_cub, &in_a, s, debug);
+        if (rc) return rc;
+        if (!in_a) {
+            SAGARS_CUDA(cudaMemcpyAsync(bv.point_list_keys, bv.keys_alt, (size_t)R * 8, cudaMemcpyDeviceToDevice, s));
+            SAGARS_CUDA(cudaMemcpyAsync(bv.point_list, bv.vals_alt, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
+        }
+    }
+    rc = launch_tile_ranges(R, num_tiles, bv.point_list_keys, im.ranges, s, debug);
+    if (rc) return rc;
+    rc = launch_render_forward(*a, d, g, im, bv.point_list, s, debug);
+    if (rc) return rc;
+    return SAGARS_OK;
+}
+
+int sagars_backward(const sagars_backward_args* a, void* stream_)
+{
+    g_err[0] = 0;
+    if (!a) { set_error("sagars_backward: NULL argument"); return SAGARS_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream_;
+    const bool debug = (a->flags & SAGARS_FLAG_DEBUG) != 0;
+    const bool mask_only = (a->flags & SAGARS_FLAG_MASK_ONLY) != 0;
+    const bool md = (a->flags & (SAGARS_FLAG_MASK_DEPTH | SAGARS_FLAG_MASK_ONLY)) != 0;
+
+    Dims d;
+    int rc = fill_dims(d, a->P, a->D, a->M, a->num_channels, a->width, a->height, a->tan_fovx, a->tan_fovy, a->scale_modifier);
+    if (rc) return rc;
+    if (a->P == 0) return SAGARS_OK;
+    if (!a->geom_buffer || !a->image_buffer || (a->R > 0 && !a->binning_buffer) || !a->grad_scratch || !a->radii ||
+        !a->means3D || !a->viewmatrix || !a->projmatrix || !a->background) {
+        set_error("sagars_backward: missing required pointer");
+        return SAGARS_EINVAL;
+    }
+    if (!mask_only && (!a->dL_dout_color || !a->dL_dcolors || !a->dL_dmeans2D || !a->dL_dopacity || !a->dL_dmeans3D ||
+                       !a->dL_dcov3D || !a->dL_dscales || !a->dL_drotations)) {
+        set_error("sagars_backward: missing gradient pointer");
+        return SAGARS_EINVAL;
+    }
+    if (md && (!a->dL_dout_mask || !a->dL_dmask)) {
+        set_error("sagars_backward: dL_dout_mask / dL_dmask required for the depth variant");
+        return SAGARS_EINVAL;
+    }
+    if (a->M > 0 && a->shs != nullptr && !a->dL_dsh) {
+        set_error("sagars_backward: dL_dsh required when shs are given");
+        return SAGARS_EINVAL;
+    }
+    SAGARS_CUDA(cudaSetDevice(a->device));
+
+    GeomView g = geom_view(const_cast<void*>(a->geom_buffer), d.P);
+    ImageView im = image_view(const_cast<void*>(a->image_buffer), d.W, d.H);
+    const uint32_t* point_list = nullptr;
+    if (a->R > 0) point_list = binning_view(const_cast<void*>(a->binning_buffer), (size_t)a->R).point_list;
+    float* ggrad = (float*)a->grad_scratch;
+
+    SAGARS_CUDA(cudaMemsetAsync(ggrad, 0, (size_t)d.P * GG_STRIDE * sizeof(float), s));
+    if (!mask_only) SAGARS_CUDA(cudaMemsetAsync(a->dL_dcolors, 0, (size_t)d.P * d.C * sizeof(float), s));
+    if (a->R > 0) {
+        rc = launch_render_backward(*a, d, g, im, point_list, ggrad, s, debug);
+        if (rc) return rc;
+    }
+    if (mask_only) {
+        // mask-only path: the only gradient is dL_dmask (DEPTH __init__.py:280-289)
+        SAGARS_CUDA(cudaMemcpy2DAsync(a->dL_dmask, sizeof(float), ggrad + 6, GG_STRIDE * sizeof(float), sizeof(float),
+                                      (size_t)d.P, cudaMemcpyDeviceToDevice, s));
+        return SAGARS_OK;
+    }
+    rc = launch_geom_backward(*a, d, g, ggrad, s, debug);
+    return rc;
+}
+
+int sagars_mark_visible(int32_t device, int32_t P, const float* means3D, const float* viewmatrix,
+                        const float* projmatrix, uint8_t* present, void* stream)
+{
+    g_err[0] = 0;
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) {
+        set_error("sagars_mark_visible: bad argument");
+        return SAGARS_EINVAL;
+    }
+    if (P == 0) return SAGARS_OK;
+    SAGARS_CUDA(cudaSetDevice(device));
+    return launch_mark_visible(P, means3D, viewmatrix, projmatrix, present, (cudaStream_t)stream);
+}
+
+int sagars_sort_pairs(int32_t device, int32_t n, int32_t end_bit, const uint64_t* keys_in, const uint32_t* vals_in,
+                      uint64_t* keys_out, uint32_t* vals_out, void* temp, int32_t use_cub, void* stream_)
+{
+    // stand-alone entry for tests.  `temp` layout: [keys_alt n*8][vals_alt n*4][sort temp]
+    g_err[0] = 0;
+    if (n < 0 || end_bit < 1 || end_bit > 64 || (n > 0 && (!keys_in || !vals_in || !keys_out || !vals_out || !temp))) {
+        set_error("sagars_sort_pairs: bad argument");
+        return SAGARS_EINVAL;
+    }
+    if (n == 0) return SAGARS_OK;
+    cudaStream_t s = (cudaStream_t)stream_;
+    SAGARS_CUDA(cudaSetDevice(device));
+    char* t = (char*)temp;
+    uint64_t* keys_alt = (uint64_t*)t;
+    uint32_t* vals_alt = (uint32_t*)(t + align_up((size_t)n * 8));
+    void* stemp = t + align_up((size_t)n * 8) + align_up((size_t)n * 4);
+    const bool start_alt = !use_cub && (sort_num_passes(end_bit) & 1);
+    SAGARS_CUDA(cudaMemcpyAsync(start_alt ? keys_alt : keys_out, keys_in, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+    SAGARS_CUDA(cudaMemcpyAsync(start_alt ? vals_alt : vals_out, vals_in, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    bool in_a = true;
+    int rc = launch_sort_pairs(n, end_bit, keys_out, vals_out, keys_alt, vals_alt, stemp, sort_temp_bytes((size_t)n),
+                               use_cub != 0, &in_a, s, false);
+    if (rc) return rc;
+    if (!in_a) {
+        SAGARS_CUDA(cudaMemcpyAsync(keys_out, keys_alt, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+        SAGARS_CUDA(cudaMemcpyAsync(vals_out, vals_alt, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    return SAGARS_OK;
+}
+
+}  // extern "C"

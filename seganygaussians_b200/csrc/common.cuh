@@ -1,0 +1,205 @@
+// common.cuh -- shared declarations of the sm_100a Gaussian feature rasterizer (libsagars).
+//
+// Private to the library.  The public C ABI is include/sagars.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/sagars.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libsagars carries sm_100a code only (build with -gencode arch=compute_100a,code=sm_100a)"
+#endif
+
+namespace sagars {
+
+constexpr int TILE_X = SAGARS_TILE_X;
+constexpr int TILE_Y = SAGARS_TILE_Y;
+constexpr int TILE_PIX = TILE_X * TILE_Y;   // 256 pixels = one CTA of the blend kernels
+
+// ---------------------------------------------------------------------------------------------
+// Scratch layouts.  Every field starts on a 256-byte boundary.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct GeomView {
+    float* depths;            // [P]
+    float* geo;               // [P][8]  x, y, conic.x, conic.y, conic.z, opacity, depth, 0
+    float* cov3D;             // [P][6]
+    float* rgb;               // [P][3]
+    uint8_t* clamped;         // [P][3]
+    uint32_t* tiles_touched;  // [P]
+    uint32_t* point_offsets;  // [P]  inclusive prefix sum of tiles_touched
+    uint32_t* block_sums;     // [ceil(P/256)+1]  per-preprocess-block sums, then their exclusive scan
+    uint32_t* status;         // [8]  0: prefilter violation flag, 1: num_rendered
+};
+
+struct GeomOffsets {
+    sagars_geom_layout pub;
+    size_t block_sums;
+};
+inline GeomOffsets geom_offsets(size_t P) {
+    GeomOffsets G;
+    sagars_geom_layout& L = G.pub;
+    size_t o = 0;
+    L.depths = o;        o = align_up(o + P * 4);
+    L.geo = o;           o = align_up(o + P * 32);
+    L.cov3D = o;         o = align_up(o + P * 24);
+    L.rgb = o;           o = align_up(o + P * 12);
+    L.clamped = o;       o = align_up(o + P * 3);
+    L.tiles_touched = o; o = align_up(o + P * 4);
+    L.point_offsets = o; o = align_up(o + P * 4);
+    size_t nblk = (P + 255) / 256 + 1;
+    G.block_sums = o;    o = align_up(o + nblk * 4);
+    L.status = o;        o = align_up(o + 64);
+    L.total = o + 256;
+    return G;
+}
+inline sagars_geom_layout geom_layout(size_t P) { return geom_offsets(P).pub; }
+inline GeomView geom_view(void* base, size_t P) {
+    GeomOffsets G = geom_offsets(P);
+    const sagars_geom_layout& L = G.pub;
+    char* b = (char*)base;
+    GeomView g;
+    g.depths = (float*)(b + L.depths);
+    g.geo = (float*)(b + L.geo);
+    g.cov3D = (float*)(b + L.cov3D);
+    g.rgb = (float*)(b + L.rgb);
+    g.clamped = (uint8_t*)(b + L.clamped);
+    g.tiles_touched = (uint32_t*)(b + L.tiles_touched);
+    g.point_offsets = (uint32_t*)(b + L.point_offsets);
+    g.block_sums = (uint32_t*)(b + G.block_sums);
+    g.status = (uint32_t*)(b + L.status);
+    return g;
+}
+
+struct ImageView {
+    float* final_T;        // [H*W]
+    uint32_t* n_contrib;   // [H*W]
+    uint2* ranges;         // [tiles]
+};
+inline sagars_image_layout image_layout(int W, int H) {
+    sagars_image_layout L;
+    size_t N = (size_t)W * H;
+    size_t T = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
+    size_t o = 0;
+    L.final_T = o;   o = align_up(o + N * 4);
+    L.n_contrib = o; o = align_up(o + N * 4);
+    L.ranges = o;    o = align_up(o + T * 8);
+    L.total = o + 256;
+    return L;
+}
+inline ImageView image_view(void* base, int W, int H) {
+    sagars_image_layout L = image_layout(W, H);
+    char* b = (char*)base;
+    ImageView v;
+    v.final_T = (float*)(b + L.final_T);
+    v.n_contrib = (uint32_t*)(b + L.n_contrib);
+    v.ranges = (uint2*)(b + L.ranges);
+    return v;
+}
+
+// Radix sort scratch: ping-pong key/value buffers + per-block digit counts.
+constexpr int SORT_CHUNK = 4096;          // keys per sort block
+constexpr int SORT_RADIX_BITS = 8;
+constexpr int SORT_RADIX = 1 << SORT_RADIX_BITS;
+
+struct BinningView {
+    uint32_t* point_list;        // [R] sorted values (final)
+    uint64_t* point_list_keys;   // [R] sorted keys (final)
+    uint32_t* vals_alt;          // [R]
+    uint64_t* keys_alt;          // [R]
+    void* sort_temp;             // sort_temp_bytes(R)
+};
+inline size_t sort_temp_bytes(size_t n) {
+    size_t nblk = (n + SORT_CHUNK - 1) / SORT_CHUNK;
+    // own sort: counts[RADIX][nblk] + totals[RADIX];  CUB (DoubleBuffer) needs O(n / tile) look-back state
+    size_t own = align_up((size_t)SORT_RADIX * (nblk + 1) * 4) + align_up(SORT_RADIX * 4);
+    size_t cub = align_up(n / 2 + (1u << 20));
+    return own > cub ? own : cub;
+}
+inline sagars_binning_layout binning_layout(size_t R) {
+    sagars_binning_layout L;
+    size_t o = 0;
+    L.point_list = o;      o = align_up(o + R * 4);
+    L.point_list_keys = o; o = align_up(o + R * 8);
+    L.total = o;   // (extended below; `total` is patched by binning_total)
+    return L;
+}
+inline size_t binning_total(size_t R) {
+    size_t o = binning_layout(R).total;
+    o = align_up(o + R * 4);   // vals_alt
+    o = align_up(o + R * 8);   // keys_alt
+    o = align_up(o + sort_temp_bytes(R));
+    return o + 256;
+}
+inline BinningView binning_view(void* base, size_t R) {
+    sagars_binning_layout L = binning_layout(R);
+    char* b = (char*)base;
+    BinningView v;
+    v.point_list = (uint32_t*)(b + L.point_list);
+    v.point_list_keys = (uint64_t*)(b + L.point_list_keys);
+    size_t o = L.total;
+    v.vals_alt = (uint32_t*)(b + o); o = align_up(o + R * 4);
+    v.keys_alt = (uint64_t*)(b + o); o = align_up(o + R * 8);
+    v.sort_temp = (void*)(b + o);
+    return v;
+}
+
+// Per-Gaussian accumulators of the blend backward: 8 floats per Gaussian
+//   0: dL/dmean2D.x  1: dL/dmean2D.y  2: dL/dconic.x  3: dL/dconic.y  4: dL/dconic.w(zz)
+//   5: dL/dopacity   6: dL/dmask      7: unused
+constexpr int GG_STRIDE = 8;
+inline size_t grad_scratch_bytes(size_t P) { return align_up(P * GG_STRIDE * 4) + 256; }
+
+// ---------------------------------------------------------------------------------------------
+// error handling (thread-local message, returned through sagars_last_error)
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+void count_launch(int n = 1);
+
+#define SAGARS_CUDA(call)                                                         \
+    do {                                                                          \
+        cudaError_t _e = (call);                                                  \
+        if (_e != cudaSuccess) return ::sagars::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// after a kernel launch: always check the launch; in debug mode also synchronise and check execution
+#define SAGARS_LAUNCH_CHECK(stream, debug)                                        \
+    do {                                                                          \
+        ::sagars::count_launch();                                                 \
+        cudaError_t _e = cudaGetLastError();                                      \
+        if (_e == cudaSuccess && (debug)) _e = cudaStreamSynchronize(stream);     \
+        if (_e != cudaSuccess) return ::sagars::cuda_fail(_e, "kernel", __FILE__, __LINE__); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// stage entry points (host side), one per .cu
+// ---------------------------------------------------------------------------------------------
+struct Dims {
+    int P, D, M, C, W, H;
+    int tiles_x, tiles_y;
+    float tan_fovx, tan_fovy, focal_x, focal_y, scale_modifier;
+};
+
+int launch_preprocess(const sagars_forward_args& a, const Dims& d, GeomView g, cudaStream_t s, bool debug);
+int launch_scan_block_sums(const Dims& d, GeomView g, cudaStream_t s, bool debug);
+int launch_duplicate(const Dims& d, GeomView g, const int32_t* radii, uint64_t* keys, uint32_t* vals,
+                     cudaStream_t s, bool debug);
+int launch_sort_pairs(int n, int end_bit, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b,
+                      uint32_t* vals_b, void* temp, size_t temp_bytes, bool use_cub, bool* result_in_a,
+                      cudaStream_t s, bool debug);
+int sort_num_passes(int end_bit);
+int launch_tile_ranges(int R, int num_tiles, const uint64_t* keys, uint2* ranges, cudaStream_t s, bool debug);
+int launch_render_forward(const sagars_forward_args& a, const Dims& d, GeomView g, ImageView im,
+                          const uint32_t* point_list, cudaStream_t s, bool debug);
+int launch_render_backward(const sagars_backward_args& a, const Dims& d, GeomView g, ImageView im,
+                           const uint32_t* point_list, float* ggrad, cudaStream_t s, bool debug);
+int launch_geom_backward(const sagars_backward_args& a, const Dims& d, GeomView g, const float* ggrad,
+                         cudaStream_t s, bool debug);
+int launch_mark_visible(int P, const float* means3D, const float* view, const float* proj, uint8_t* present,
+                        cudaStream_t s);
+
+}  // namespace sagars

@@ -1,0 +1,236 @@
+// render_forward.cu -- per-tile front-to-back alpha compositing of C feature channels
+// (+ optional mask / depth channels).
+//
+// Semantics: CF cuda_rasterizer/forward.cu:264-385 (DEPTH forward.cu:262-387 adds the mask/depth
+// accumulators), SURVEY.md Appendix A.10-A.12.  One CTA per 16x16 tile, one thread per pixel.
+// What is this library's own:
+//   * the per-instance records ({xy, conic, opacity, depth} = 32 B) and the C-float feature rows of
+//     a batch of instances are staged in shared memory by asynchronous 16-byte copies
+//     (cp.async / LDGSTS), double buffered so the copies of batch b+1 overlap the blending of batch
+//     b; the reference re-reads every feature from global memory per pixel per channel;
+//   * a warp covers an 8x4 pixel block (the reference: 16x2), which cuts the number of
+//     (warp, Gaussian) pairs that have any pixel to blend;
+//   * a warp stops as soon as its 32 pixels are saturated (the reference only stops per CTA, per
+//     256-instance batch);
+//   * C is a run-time value (<= 64), dispatched onto float4-group templates.
+// The per-pixel arithmetic (power, alpha, the 1/255 and 1e-4 tests, the order of accumulation)
+// is kept operation for operation so that n_contrib / final_T / colours match the reference.
+#include "common.cuh"
+#include "cp_async.cuh"
+
+namespace sagars {
+
+constexpr int FWD_BATCH = 64;   // instances staged per pipeline stage
+
+template <int NQ>
+struct FwdSmem {
+    float4 geo[2][FWD_BATCH][2];        // x, y, cx, cy | cz, opacity, depth, -
+    float4 feat[2][FWD_BATCH][NQ];      // feature rows, zero padded to 4*NQ channels
+    uint32_t ids[2][FWD_BATCH];
+    float maskv[2][FWD_BATCH];          // DEPTH variant: per-instance mask value
+};
+
+// issue the asynchronous copies of one batch (ids already in smem)
+template <int NQ, bool VEC, bool MD, bool COLOR>
+__device__ __forceinline__ void fwd_issue_batch(FwdSmem<NQ>& sm, int stage, int idbuf, int cnt, int K,
+                                                const float* __restrict__ geo, const float* __restrict__ features,
+                                                const float* __restrict__ mask)
+{
+    const int tid = threadIdx.x;
+    // geometry records: 2 x 16 B per instance
+    for (int c = tid; c < cnt * 2; c += TILE_PIX) {
+        const int j = c >> 1, h = c & 1;
+        const uint32_t id = sm.ids[idbuf][j];
+        cp_async16(&sm.geo[stage][j][h], geo + 8 * (size_t)id + 4 * h);
+    }
+    if (MD) {
+        if (tid < cnt) sm.maskv[stage][tid] = mask[sm.ids[idbuf][tid]];
+    }
+    if (!COLOR) return;
+    if (VEC) {
+        const int nq = K >> 2;   // == NQ or fewer (remaining quads stay zero)
+        for (int c = tid; c < cnt * nq; c += TILE_PIX) {
+            const int j = c / nq, q = c - j * nq;
+            const uint32_t id = sm.ids[idbuf][j];
+            cp_async16(&sm.feat[stage][j][q], features + (size_t)id * K + 4 * q);
+        }
+    } else {
+        float* f = reinterpret_cast<float*>(&sm.feat[stage][0][0]);
+        for (int c = tid; c < cnt * K; c += TILE_PIX) {
+            const int j = c / K, k = c - j * K;
+            const uint32_t id = sm.ids[idbuf][j];
+            f[j * (4 * NQ) + k] = features[(size_t)id * K + k];
+        }
+    }
+}
+
+template <int NQ, bool VEC, bool MD, bool COLOR>
+__global__ void __launch_bounds__(TILE_PIX)
+render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                      int W, int H, int K,
+                      const float* __restrict__ geo, const float* __restrict__ features,
+                      const float* __restrict__ mask, const float* __restrict__ bg,
+                      float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
+                      float* __restrict__ out_color, float* __restrict__ out_mask, float* __restrict__ out_depth)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FwdSmem<NQ>& sm = *reinterpret_cast<FwdSmem<NQ>*>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles_x = gridDim.x;
+    const uint32_t px = blockIdx.x * TILE_X + (warp & 1) * 8 + (lane & 7);
+    const uint32_t py = blockIdx.y * TILE_Y + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = px < (uint32_t)W && py < (uint32_t)H;
+    const uint32_t pix_id = (uint32_t)W * py + px;
+    const float pixx = (float)px, pixy = (float)py;
+
+    const uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];
+    const int total = (int)(range.y - range.x);
+    const int nbatch = (total + FWD_BATCH - 1) / FWD_BATCH;
+
+    // zero the padded feature channels once (cp.async only ever writes the first K of each row)
+    if (!VEC || (K >> 2) < NQ) {
+        float* f = reinterpret_cast<float*>(&sm.feat[0][0][0]);
+        for (int c = tid; c < 2 * FWD_BATCH * 4 * NQ; c += TILE_PIX) f[c] = 0.f;
+    }
+
+    float T = 1.0f;
+    uint32_t last_contributor = 0;
+    float C[4 * NQ];
+#pragma unroll
+    for (int k = 0; k < 4 * NQ; k++) C[k] = 0.f;
+    float Macc = 0.f, Dacc = 0.f;
+    bool done = !inside;
+
+    // prologue: ids(0) -> smem, copies of batch 0, ids(1) -> smem
+    if (nbatch > 0) {
+        if (tid < min(FWD_BATCH, total)) sm.ids[0][tid] = point_list[range.x + tid];
+        __syncthreads();
+        fwd_issue_batch<NQ, VEC, MD, COLOR>(sm, 0, 0, min(FWD_BATCH, total), K, geo, features, mask);
+        cp_async_commit();
+        if (nbatch > 1 && tid < min(FWD_BATCH, total - FWD_BATCH)) sm.ids[1][tid] = point_list[range.x + FWD_BATCH + tid];
+        cp_async_wait_all();
+        __syncthreads();
+    }
+
+    for (int b = 0; b < nbatch; b++) {
+        const int stage = b & 1;
+        const int cnt = min(FWD_BATCH, total - b * FWD_BATCH);
+        // all pixels of the tile saturated -> nothing left to do (block-uniform)
+        if (__syncthreads_and(done)) break;
+
+        // (A) start the copies of batch b+1 (its ids were stored one iteration ago)
+        if (b + 1 < nbatch) {
+            fwd_issue_batch<NQ, VEC, MD, COLOR>(sm, stage ^ 1, (b + 1) & 1, min(FWD_BATCH, total - (b + 1) * FWD_BATCH),
+                                         K, geo, features, mask);
+            cp_async_commit();
+        }
+        // (B) ids of batch b+2 into a register
+        uint32_t next_id = 0;
+        const int rem2 = total - (b + 2) * FWD_BATCH;
+        const bool have_next_id = (b + 2 < nbatch) && tid < min(FWD_BATCH, rem2);
+        if (have_next_id) next_id = point_list[range.x + (b + 2) * FWD_BATCH + tid];
+
+        // (C) blend batch b
+        if (!__all_sync(0xffffffffu, done)) {
+            for (int j = 0; j < cnt; j++) {
+                if (!done) {
+                    const float4 g0 = sm.geo[stage][j][0];
+                    const float4 g1 = sm.geo[stage][j][1];
+                    const float dx = g0.x - pixx, dy = g0.y - pixy;
+                    const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
+                    if (!(power > 0.0f)) {
+                        const float alpha = fminf(0.99f, g1.y * expf(power));
+                        if (!(alpha < 1.0f / 255.0f)) {
+                            const float test_T = T * (1 - alpha);
+                            if (test_T < 0.0001f) {
+                                done = true;
+                            } else {
+                                if (COLOR) {
+#pragma unroll
+                                    for (int q = 0; q < NQ; q++) {
+                                        const float4 f = sm.feat[stage][j][q];
+                                        C[4 * q + 0] += f.x * alpha * T;
+                                        C[4 * q + 1] += f.y * alpha * T;
+                                        C[4 * q + 2] += f.z * alpha * T;
+                                        C[4 * q + 3] += f.w * alpha * T;
+                                    }
+                                }
+                                if (MD) {
+                                    Macc += sm.maskv[stage][j] * alpha * T;
+                                    Dacc += g1.z * alpha * T;
+                                }
+                                T = test_T;
+                                last_contributor = (uint32_t)(b * FWD_BATCH + j + 1);
+                            }
+                        }
+                    }
+                }
+                if ((j & 7) == 7 && __all_sync(0xffffffffu, done)) break;
+            }
+        }
+
+        // (D) publish ids(b+2); wait for batch b+1
+        if (have_next_id) sm.ids[b & 1][tid] = next_id;
+        cp_async_wait_all();
+        __syncthreads();
+    }
+
+    if (inside) {
+        final_T[pix_id] = T;
+        n_contrib[pix_id] = last_contributor;
+        const size_t plane = (size_t)H * W;
+        if (COLOR) {
+#pragma unroll
+            for (int k = 0; k < 4 * NQ; k++)
+                if (k < K) out_color[(size_t)k * plane + pix_id] = C[k] + T * bg[k];
+        }
+        if (MD) {
+            out_mask[pix_id] = Macc;
+            if (out_depth != nullptr) out_depth[pix_id] = Dacc;
+        }
+    }
+}
+
+template <int NQ, bool VEC, bool MD, bool COLOR>
+static int launch_fwd_t(const sagars_forward_args& a, const Dims& d, GeomView g, ImageView im,
+                        const uint32_t* point_list, const float* features, cudaStream_t s, bool debug)
+{
+    auto kern = render_forward_kernel<NQ, VEC, MD, COLOR>;
+    const size_t smem = sizeof(FwdSmem<NQ>);
+    SAGARS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(d.tiles_x, d.tiles_y);
+    kern<<<grid, TILE_PIX, smem, s>>>(im.ranges, point_list, d.W, d.H, d.C, g.geo, features, a.mask, a.background,
+                                      im.final_T, im.n_contrib, a.out_color, a.out_mask, a.out_depth);
+    SAGARS_LAUNCH_CHECK(s, debug);
+    return SAGARS_OK;
+}
+
+int launch_render_forward(const sagars_forward_args& a, const Dims& d, GeomView g, ImageView im,
+                          const uint32_t* point_list, cudaStream_t s, bool debug)
+{
+    const bool md = (a.flags & SAGARS_FLAG_MASK_DEPTH) != 0;
+    const bool mask_only = (a.flags & SAGARS_FLAG_MASK_ONLY) != 0;
+    const float* features = a.colors_precomp != nullptr ? a.colors_precomp : g.rgb;
+    const int K = d.C;
+    if (mask_only) return launch_fwd_t<1, false, true, false>(a, d, g, im, point_list, features, s, debug);
+    const bool vec = (K % 4) == 0;
+    const int nq = (K + 3) / 4;
+#define SAGARS_FWD_CASE(NQ_)                                                                               \
+    if (nq <= NQ_) {                                                                                       \
+        if (md) return vec ? launch_fwd_t<NQ_, true, true, true>(a, d, g, im, point_list, features, s, debug) \
+                           : launch_fwd_t<NQ_, false, true, true>(a, d, g, im, point_list, features, s, debug); \
+        return vec ? launch_fwd_t<NQ_, true, false, true>(a, d, g, im, point_list, features, s, debug)       \
+                   : launch_fwd_t<NQ_, false, false, true>(a, d, g, im, point_list, features, s, debug);     \
+    }
+    SAGARS_FWD_CASE(1)
+    SAGARS_FWD_CASE(2)
+    SAGARS_FWD_CASE(4)
+    SAGARS_FWD_CASE(8)
+    SAGARS_FWD_CASE(16)
+#undef SAGARS_FWD_CASE
+    set_error("unsupported channel count %d (max %d)", K, SAGARS_MAX_CHANNELS);
+    return SAGARS_EINVAL;
+}
+
+}  // namespace sagars
