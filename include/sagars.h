@@ -214,10 +214,19 @@ SAGARS_API int sagars_sort_pairs(int32_t device, int32_t n, int32_t end_bit,
                       uint64_t* keys_out, uint32_t* vals_out,
                       void* temp, int32_t use_cub, void* stream);
 
-/* number of kernels launched by this library on the calling thread since the last reset
+/* number of kernels launched by this library (process-wide) since the last reset
  * (bench.py reports it as `gpu_launches`). */
 SAGARS_API int64_t sagars_launch_count(void);
 SAGARS_API void sagars_reset_launch_count(void);
+
+/* Optional per-stage device timing: when enabled, every stage of forward / backward is bracketed by CUDA
+ * events recorded on the caller's stream.  sagars_profile_read() waits for the recorded events and
+ * returns accumulated milliseconds / launch counts per stage (bench.py derives the roofline of the
+ * dominant kernel from these). */
+SAGARS_API void sagars_profile_enable(int on);
+SAGARS_API int sagars_profile_num_stages(void);
+SAGARS_API const char* sagars_profile_stage_name(int stage);
+SAGARS_API int sagars_profile_read(double* ms_out, int64_t* count_out, int reset);
 
 SAGARS_API const char* sagars_last_error(void);
 SAGARS_API int sagars_abi_version(void);

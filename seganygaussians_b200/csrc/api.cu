@@ -7,11 +7,14 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
+#include <mutex>
+#include <vector>
 
 namespace sagars {
 
 static thread_local char g_err[512] = "";
-static thread_local int64_t g_launches = 0;
+static std::atomic<int64_t> g_launches{0};   // process-wide: autograd runs backward on its own thread
 
 void set_error(const char* fmt, ...)
 {
@@ -28,7 +31,44 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
     return SAGARS_ECUDA;
 }
 
-void count_launch(int n) { g_launches += n; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- optional per-stage device timing (CUDA events on the caller's stream), for bench.py's roofline ----
+enum Stage { ST_PREPROCESS = 0, ST_SCAN, ST_DUPLICATE, ST_SORT, ST_RANGES, ST_RENDER_FWD, ST_RENDER_BWD, ST_GEOM_BWD, ST_COUNT };
+static const char* kStageNames[ST_COUNT] = {"preprocess", "scan_block_sums", "duplicate_keys", "radix_sort", "tile_ranges",
+                                            "render_forward", "render_backward", "geom_backward"};
+struct ProfRec { int stage; cudaEvent_t a, b; };
+static std::atomic<int> g_profile{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+static double g_prof_ms[ST_COUNT];
+static int64_t g_prof_n[ST_COUNT];
+
+static cudaEvent_t prof_event()
+{
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+struct ProfScope {
+    int stage; cudaStream_t s; cudaEvent_t a = nullptr, b = nullptr; bool on;
+    ProfScope(int stage_, cudaStream_t s_) : stage(stage_), s(s_), on(g_profile.load() != 0)
+    {
+        if (!on) return;
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        a = prof_event(); b = prof_event();
+        cudaEventRecord(a, s);
+    }
+    ~ProfScope()
+    {
+        if (!on) return;
+        cudaEventRecord(b, s);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof_recs.push_back({stage, a, b});
+    }
+};
 
 // same rule as the reference's getHigherMsb (CF rasterizer_impl.cu:35-50): bits needed for tile ids
 static uint32_t higher_msb(uint32_t n)
@@ -71,10 +111,34 @@ using namespace sagars;
 extern "C" {
 
 int sagars_abi_version(void) { return SAGARS_ABI_VERSION; }
+
+void sagars_profile_enable(int on) { g_profile.store(on ? 1 : 0); }
+int sagars_profile_num_stages(void) { return ST_COUNT; }
+const char* sagars_profile_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : ""; }
+int sagars_profile_read(double* ms_out, int64_t* count_out, int reset)
+{
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof_recs) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            g_prof_ms[r.stage] += ms;
+            g_prof_n[r.stage] += 1;
+        }
+        g_prof_pool.push_back(r.a);
+        g_prof_pool.push_back(r.b);
+    }
+    g_prof_recs.clear();
+    for (int i = 0; i < ST_COUNT; i++) {
+        if (ms_out) ms_out[i] = g_prof_ms[i];
+        if (count_out) count_out[i] = g_prof_n[i];
+        if (reset) { g_prof_ms[i] = 0.0; g_prof_n[i] = 0; }
+    }
+    return SAGARS_OK;
+}
 const char* sagars_arch(void) { return "sm_100a"; }
 const char* sagars_last_error(void) { return g_err; }
-int64_t sagars_launch_count(void) { return g_launches; }
-void sagars_reset_launch_count(void) { g_launches = 0; }
+int64_t sagars_launch_count(void) { return g_launches.load(); }
+void sagars_reset_launch_count(void) { g_launches.store(0); }
 
 size_t sagars_geom_bytes(int32_t P) { return geom_layout((size_t)(P < 0 ? 0 : P)).total; }
 size_t sagars_image_bytes(int32_t W, int32_t H) { return image_layout(W, H).total; }
@@ -160,9 +224,9 @@ int sagars_forward(const sagars_forward_args* a,
     ImageView im = image_view(img_mem, d.W, d.H);
 
     SAGARS_CUDA(cudaMemsetAsync(g.status, 0, 64, s));
-    rc = launch_preprocess(*a, d, g, s, debug);
+    { ProfScope ps(ST_PREPROCESS, s); rc = launch_preprocess(*a, d, g, s, debug); }
     if (rc) return rc;
-    rc = launch_scan_block_sums(d, g, s, debug);
+    { ProfScope ps(ST_SCAN, s); rc = launch_scan_block_sums(d, g, s, debug); }
     if (rc) return rc;
 
     // the one host synchronisation of the forward pass: R sizes the binning buffer
@@ -188,20 +252,23 @@ int sagars_forward(const sagars_forward_args* a,
         const bool start_alt = !use_cub && (sort_num_passes(end_bit) & 1);
         uint64_t* k0 = start_alt ? bv.keys_alt : bv.point_list_keys;
         uint32_t* v0 = start_alt ? bv.vals_alt : bv.point_list;
-        rc = launch_duplicate(d, g, a->radii, k0, v0, s, debug);
+        { ProfScope ps(ST_DUPLICATE, s); rc = launch_duplicate(d, g, a->radii, k0, v0, s, debug); }
         if (rc) return rc;
         bool in_a = true;
-        rc = launch_sort_pairs(R, end_bit, bv.point_list_keys, bv.point_list, bv.keys_alt, bv.vals_alt, bv.sort_temp,
-                               sort_temp_bytes((size_t)R), use_cub, &in_a, s, debug);
+        {
+            ProfScope ps(ST_SORT, s);
+            rc = launch_sort_pairs(R, end_bit, bv.point_list_keys, bv.point_list, bv.keys_alt, bv.vals_alt, bv.sort_temp,
+                                   sort_temp_bytes((size_t)R), use_cub, &in_a, s, debug);
+        }
         if (rc) return rc;
         if (!in_a) {
             SAGARS_CUDA(cudaMemcpyAsync(bv.point_list_keys, bv.keys_alt, (size_t)R * 8, cudaMemcpyDeviceToDevice, s));
             SAGARS_CUDA(cudaMemcpyAsync(bv.point_list, bv.vals_alt, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
         }
     }
-    rc = launch_tile_ranges(R, num_tiles, bv.point_list_keys, im.ranges, s, debug);
+    { ProfScope ps(ST_RANGES, s); rc = launch_tile_ranges(R, num_tiles, bv.point_list_keys, im.ranges, s, debug); }
     if (rc) return rc;
-    rc = launch_render_forward(*a, d, g, im, bv.point_list, s, debug);
+    { ProfScope ps(ST_RENDER_FWD, s); rc = launch_render_forward(*a, d, g, im, bv.point_list, s, debug); }
     if (rc) return rc;
     return SAGARS_OK;
 }
@@ -248,7 +315,7 @@ int sagars_backward(const sagars_backward_args* a, void* stream_)
     SAGARS_CUDA(cudaMemsetAsync(ggrad, 0, (size_t)d.P * GG_STRIDE * sizeof(float), s));
     if (!mask_only) SAGARS_CUDA(cudaMemsetAsync(a->dL_dcolors, 0, (size_t)d.P * d.C * sizeof(float), s));
     if (a->R > 0) {
-        rc = launch_render_backward(*a, d, g, im, point_list, ggrad, s, debug);
+        { ProfScope ps(ST_RENDER_BWD, s); rc = launch_render_backward(*a, d, g, im, point_list, ggrad, s, debug); }
         if (rc) return rc;
     }
     if (mask_only) {
@@ -257,7 +324,7 @@ int sagars_backward(const sagars_backward_args* a, void* stream_)
                                       (size_t)d.P, cudaMemcpyDeviceToDevice, s));
         return SAGARS_OK;
     }
-    rc = launch_geom_backward(*a, d, g, ggrad, s, debug);
+    { ProfScope ps(ST_GEOM_BWD, s); rc = launch_geom_backward(*a, d, g, ggrad, s, debug); }
     return rc;
 }
 
