@@ -193,7 +193,8 @@ def main():
             t.grad = None
         color, radii = rast_resident(means3D=means3D, means2D=means2D, opacities=opac, shs=None, colors_precomp=colors,
                                      scales=scales, rotations=rots, cov3D_precomp=None)
-        last["fn"] = color.grad_fn
+        last["num_rendered"] = int(color.grad_fn.num_rendered)
+        last["radii"] = radii
         color.backward(dL)
         if use_dist:
             dist.all_reduce(colors.grad)
@@ -263,9 +264,8 @@ def main():
         return 0
 
     # ---------------- work counters of rank 0's camera ----------------
-    fn = last["fn"]
-    R_inst = int(fn.num_rendered)
-    radii_vis = int((fn.saved_tensors[5] > 0).sum().item())
+    R_inst = last["num_rendered"]
+    radii_vis = int((last["radii"] > 0).sum().item())
     T_tiles = ((W + 15) // 16) * ((H + 15) // 16)
     line = {
         "metric": "fwd+bwd Gaussians*pixels/s @K=32", "value": value, "unit": "Gaussian*pixel/s",

@@ -7,6 +7,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <ctime>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -69,6 +71,20 @@ struct ProfScope {
         g_prof_recs.push_back({stage, a, b});
     }
 };
+
+// host-side trace of the forward's phases (SAGARS_TRACE=1): where does wall time go between launches?
+static bool trace_on()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SAGARS_TRACE"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+static double now_us()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
 
 // same rule as the reference's getHigherMsb (CF rasterizer_impl.cu:35-50): bits needed for tile ids
 static uint32_t higher_msb(uint32_t n)
@@ -215,6 +231,8 @@ int sagars_forward(const sagars_forward_args* a,
         set_error("sagars_forward: mask / out_mask required for the depth variant");
         return SAGARS_EINVAL;
     }
+    const bool tr = trace_on();
+    double t0 = tr ? now_us() : 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
     SAGARS_CUDA(cudaSetDevice(a->device));
 
     void* geom_mem = geom_alloc(geom_user, geom_layout(d.P).total);
@@ -223,6 +241,7 @@ int sagars_forward(const sagars_forward_args* a,
     GeomView g = geom_view(geom_mem, d.P);
     ImageView im = image_view(img_mem, d.W, d.H);
 
+    if (tr) t1 = now_us();
     SAGARS_CUDA(cudaMemsetAsync(g.status, 0, 64, s));
     { ProfScope ps(ST_PREPROCESS, s); rc = launch_preprocess(*a, d, g, s, debug); }
     if (rc) return rc;
@@ -231,8 +250,10 @@ int sagars_forward(const sagars_forward_args* a,
 
     // the one host synchronisation of the forward pass: R sizes the binning buffer
     uint32_t status_h[2] = {0, 0};
+    if (tr) t2 = now_us();
     SAGARS_CUDA(cudaMemcpyAsync(status_h, g.status, sizeof(status_h), cudaMemcpyDeviceToHost, s));
     SAGARS_CUDA(cudaStreamSynchronize(s));
+    if (tr) t3 = now_us();
     if (status_h[0] != 0) {
         set_error("Point is filtered although prefiltered is set. This shouldn't happen!");
         return SAGARS_EPREFILTER;
@@ -243,6 +264,7 @@ int sagars_forward(const sagars_forward_args* a,
     void* bin_mem = binning_alloc(binning_user, binning_total((size_t)R));
     if (!bin_mem) { set_error("allocator callback returned NULL"); return SAGARS_EALLOC; }
     BinningView bv = binning_view(bin_mem, (size_t)R);
+    if (tr) t4 = now_us();
 
     const int num_tiles = d.tiles_x * d.tiles_y;
     const int end_bit = 32 + (int)higher_msb((uint32_t)num_tiles);
@@ -270,6 +292,11 @@ int sagars_forward(const sagars_forward_args* a,
     if (rc) return rc;
     { ProfScope ps(ST_RENDER_FWD, s); rc = launch_render_forward(*a, d, g, im, bv.point_list, s, debug); }
     if (rc) return rc;
+    if (tr) {
+        t5 = now_us();
+        fprintf(stderr, "[sagars trace] fwd host us: alloc(geom,img)=%.0f launch(pre,scan)=%.0f d2h+sync=%.0f alloc(binning)=%.0f "
+                        "launch(rest)=%.0f total=%.0f\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t5 - t0);
+    }
     return SAGARS_OK;
 }
 

@@ -219,7 +219,9 @@ def run_oracle(sc, K: int, depth: bool = False, use_sh: bool = False, sh_degree:
     o.out_depth = fw.out_depth if depth else None
     o.tiles_touched, o.point_offsets, o.num_rendered = fw.tiles_touched, fw.point_offsets, fw.num_rendered
     o.point_list, o.keys, o.ranges = fw.point_list, fw.keys, fw.ranges
-    o.means2D, o.conic_opacity, o.depths, o.cov3D = fw.means2D, fw.conic_opacity, fw.depths, fw.cov3D
+    vis = fw.radii > 0   # per-Gaussian scratch of culled Gaussians is unspecified in every implementation
+    o.means2D, o.conic_opacity, o.depths, o.cov3D = (np.where(vis[:, None], fw.means2D, 0), np.where(vis[:, None], fw.conic_opacity, 0),
+                                                      np.where(vis, fw.depths, 0), np.where(vis[:, None], fw.cov3D, 0))
     if backward:
         bw = oracle.backward(fw, sc.dL_dout[:K].numpy(), sc.dL_dmask.numpy() if depth else None, nthreads=nthreads)
         o.g_means3D, o.g_means2D, o.g_opacity = bw.means3D, bw.means2D, bw.opacity

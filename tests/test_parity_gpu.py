@@ -1,0 +1,230 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA path, driven through the reference-shaped operator
+API (which calls the C ABI), against (1) the CPU oracle on seeded inputs, (2) golden vectors of the unmodified
+reference, (3) the unmodified reference extension itself when oracle/_ref is present, and (4) size-independent
+properties at BASELINE.json's full size.  Integer state is compared exactly; fp32 within RTOL=1e-4 (tests/common.py)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests import common
+from seganygaussians_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _native_library_loaded():
+    from seganygaussians_b200 import _lib
+    _lib.load()           # fails loudly when libsagars.so is missing: no fallback
+    assert torch.cuda.is_available()
+
+
+SMALL = [
+    # name, P, H, W, K, depth, use_sh, deg, M
+    ("cf_small", 3000, 72, 104, 32, False, False, 0, 0),
+    ("base_small", 3000, 72, 104, 3, False, False, 0, 0),
+    ("depth_small", 3000, 72, 104, 3, True, False, 0, 0),
+    ("base_sh3", 2000, 64, 80, 3, False, True, 3, 16),
+    ("base_sh1", 1000, 48, 64, 3, False, True, 1, 16),
+    ("depth_sh3", 2000, 64, 80, 3, True, True, 3, 16),
+    ("cf_ragged", 2500, 75, 101, 32, False, False, 0, 0),     # image not a multiple of the 16x16 tile
+    ("k16", 1500, 64, 64, 16, False, False, 0, 0),
+    ("k64", 1200, 48, 80, 64, False, False, 0, 0),
+    ("k5", 1200, 48, 80, 5, False, False, 0, 0),              # channel count that is not a multiple of 4
+    ("one_tile", 300, 16, 16, 32, False, False, 0, 0),
+]
+
+
+@pytest.mark.parametrize("cfg", SMALL, ids=[c[0] for c in SMALL])
+def test_cuda_matches_oracle(cfg):
+    _, P, H, W, K, depth, use_sh, deg, M = cfg
+    sc = synthetic.scene(P, H, W, K, sh_coeffs=M)
+    ours = common.run_torch_impl("ours", sc, K, depth=depth, use_sh=use_sh, sh_degree=deg)
+    orc = common.run_oracle(sc, K, depth=depth, use_sh=use_sh, sh_degree=deg)
+    ok, lines = common.compare(ours, orc, floats=common.FLOAT_FWD + common.GRADS + ("means2D", "conic_opacity", "depths", "cov3D"),
+                               verbose=False)
+    assert ok, "\n".join(lines)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_cuda_matches_reference_golden(path):
+    z = np.load(path)
+    P, H, W, K, depth, use_sh, deg, M = [int(v) for v in z["config"]]
+    sc = synthetic.scene(P, H, W, K, sh_coeffs=M)
+    ours = common.run_torch_impl("ours", sc, K, depth=bool(depth), use_sh=bool(use_sh), sh_degree=deg)
+    ref = common.SimpleNamespace(kind="golden(reference)", variant=ours.variant)
+    for f in z.files:
+        if f != "config":
+            setattr(ref, f, z[f])
+    ref.num_rendered = int(z["num_rendered"])
+    ok, lines = common.compare(ours, ref, floats=common.FLOAT_FWD + common.GRADS + ("means2D", "conic_opacity", "depths", "cov3D"),
+                               verbose=False)
+    assert ok, "\n".join(lines)
+
+
+LIVE_REF = [("cf_medium", 200000, 540, 960, 32, False), ("base_medium", 100000, 400, 640, 3, False),
+            ("depth_medium", 100000, 400, 640, 3, True), ("cf_full_c2", 1000000, 1080, 1920, 32, False)]
+
+
+@pytest.mark.parametrize("cfg", LIVE_REF, ids=[c[0] for c in LIVE_REF])
+def test_cuda_matches_live_reference(cfg):
+    """Against the unmodified reference extension on the same GPU, up to BASELINE.json's full size (c2)."""
+    _, P, H, W, K, depth = cfg
+    if not common.have_ref(common.variant_of(K, depth)):
+        pytest.skip("oracle/_ref not built (python oracle/build_ref.py where /root/reference is mounted)")
+    sc = synthetic.scene(P, H, W, K)
+    ours = common.run_torch_impl("ours", sc, K, depth=depth)
+    ref = common.run_torch_impl("ref", sc, K, depth=depth)
+    ok, lines = common.compare(ours, ref, floats=common.FLOAT_FWD + common.GRADS + ("means2D", "conic_opacity", "depths", "cov3D"),
+                               verbose=False)
+    assert ok, "\n".join(lines)
+    # forward images are not merely close: the per-pixel arithmetic is kept operation for operation
+    assert np.array_equal(ours.color, ref.color) and np.array_equal(ours.final_T, ref.final_T)
+
+
+def _render(sc, K, colors=None, bg=None, opac=None, cov_precomp=None, use_cub=False, debug=False, backward=False, dL=None):
+    from seganygaussians_b200 import rasterizer as R
+    dev = torch.device("cuda", 0)
+    g, c = sc.gauss, sc.cam
+    R.set_cub_sort(use_cub)
+    try:
+        Rast = R.GaussianRasterizer if K == 3 else R.GaussianRasterizerContrastiveF
+        bg_t = torch.zeros(max(K, 3)) if bg is None else bg
+        rs = R.GaussianRasterizationSettings(sc.H, sc.W, c.tanfovx, c.tanfovy, bg_t.to(dev), 1.0, c.world_view_transform.to(dev),
+                                             c.full_proj_transform.to(dev), 0, c.camera_center.to(dev), False, debug)
+        col = (g.colors if colors is None else colors).to(dev).requires_grad_(backward)
+        kw = dict(scales=g.scales.to(dev), rotations=g.rotations.to(dev)) if cov_precomp is None else dict(cov3D_precomp=cov_precomp.to(dev))
+        color, radii = Rast(rs)(means3D=g.means3D.to(dev), means2D=torch.zeros(sc.P, 3, device=dev),
+                                opacities=(g.opacities if opac is None else opac).to(dev), colors_precomp=col, **kw)
+        if backward:
+            color.backward(dL.to(dev))
+            torch.cuda.synchronize()
+            return color.detach().cpu(), radii.cpu(), col.grad.cpu()
+        torch.cuda.synchronize()
+        return color.detach().cpu(), radii.cpu(), color.grad_fn
+    finally:
+        R.set_cub_sort(False)
+
+
+def test_full_size_properties():
+    """Size-independent properties at BASELINE.json's headline size (1M Gaussians, 1080x1920, K=32)."""
+    P, H, W, K = 1_000_000, 1080, 1920, 32
+    sc = synthetic.scene(P, H, W, K)
+    ones = torch.ones(P, K)
+    col, radii, fn = _render(sc, K, colors=ones)
+    from seganygaussians_b200 import _lib
+    geom, binning, img = fn.saved_tensors[-3:]
+    R_ = int(fn.num_rendered)
+    il, bl, gl = _lib.image_layout(W, H), _lib.binning_layout(R_), _lib.geom_layout(P)
+    final_T = img[il.final_T: il.final_T + 4 * H * W].view(torch.float32).view(H, W).cpu()
+    # X5 partition of unity: features == 1, bg == 0  ->  out == 1 - final_T on every channel
+    assert torch.allclose(col[0], 1.0 - final_T, rtol=0, atol=3e-6) and torch.equal(col[0], col[K - 1])
+    # sortedness + stability of the binning, and ranges partition the list
+    keys = binning[bl.point_list_keys: bl.point_list_keys + 8 * R_].view(torch.int64)
+    vals = binning[bl.point_list: bl.point_list + 4 * R_].view(torch.int32)
+    assert bool((keys[1:] >= keys[:-1]).all())
+    same = keys[1:] == keys[:-1]
+    assert bool((vals[1:][same] > vals[:-1][same]).all())
+    tiles_touched = geom[gl.tiles_touched: gl.tiles_touched + 4 * P].view(torch.int32)
+    assert int(tiles_touched.sum()) == R_
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    ranges = img[il.ranges: il.ranges + 8 * T].view(torch.int32).view(T, 2).long()
+    assert int((ranges[:, 1] - ranges[:, 0]).sum()) == R_
+    # idempotence: the forward is deterministic to the bit
+    col2, _, _ = _render(sc, K, colors=ones)
+    assert torch.equal(col, col2)
+    # the library's sort and cub::DeviceRadixSort give the same image bits
+    col3, _, _ = _render(sc, K, colors=ones, use_cub=True)
+    assert torch.equal(col, col3)
+
+
+def test_channel_independence_k32_vs_k3():
+    """X1: the first three channels of a K=32 render equal the K=3 render of those channels, bit for bit."""
+    sc = synthetic.scene(50000, 270, 480, 32)
+    c32, r32, _ = _render(sc, 32)
+    c3, r3, _ = _render(sc, 3, colors=sc.gauss.colors[:, :3].contiguous())
+    assert torch.equal(c32[:3], c3) and torch.equal(r32, r3)
+
+
+def test_backward_linearity_full_gradient():
+    sc = synthetic.scene(30000, 200, 320, 32)
+    g1 = torch.randn(32, 200, 320, generator=torch.Generator().manual_seed(3)) / 64000
+    g2 = torch.randn(32, 200, 320, generator=torch.Generator().manual_seed(4)) / 64000
+    _, _, a = _render(sc, 32, backward=True, dL=g1)
+    _, _, b = _render(sc, 32, backward=True, dL=g2)
+    _, _, ab = _render(sc, 32, backward=True, dL=2.0 * g1 - 0.5 * g2)
+    assert float((2.0 * a - 0.5 * b - ab).abs().max()) <= 1e-4 * float(ab.abs().max())
+
+
+def test_cov3d_precomp_path_matches_scale_rotation_path():
+    """X3: the reference's own Python covariance (build_covariance_from_scaling_rotation) as cov3D_precomp."""
+    sc = synthetic.scene(20000, 160, 240, 3)
+    g = sc.gauss
+    q = g.rotations
+    r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    Rm = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                      2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                      2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], dim=1).view(-1, 3, 3)
+    L = Rm * g.scales[:, None, :]
+    S = L @ L.transpose(1, 2)
+    cov = torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], dim=1).contiguous()
+    a, ra, _ = _render(sc, 3, colors=g.colors[:, :3].contiguous())
+    b, rb, _ = _render(sc, 3, colors=g.colors[:, :3].contiguous(), cov_precomp=cov)
+    assert float((ra != rb).float().mean()) < 1e-3          # radii may flip on fp32 rounding of the covariance
+    assert float((a - b).abs().max()) < 5e-3 and float((a - b).abs().mean()) < 1e-5
+
+
+def test_edge_cases():
+    from seganygaussians_b200 import rasterizer as R
+    dev = torch.device("cuda", 0)
+    sc = synthetic.scene(64, 40, 56, 32)
+    c = sc.cam
+    bg = torch.linspace(0.1, 1.0, 32)
+    rs = R.GaussianRasterizationSettings(40, 56, c.tanfovx, c.tanfovy, bg.to(dev), 1.0, c.world_view_transform.to(dev),
+                                         c.full_proj_transform.to(dev), 0, c.camera_center.to(dev), False, True)  # debug=True
+    rast = R.GaussianRasterizerContrastiveF(rs)
+    # P == 0: zero-filled outputs, nothing launched (reference rasterize_points.cu:81)
+    e = lambda *s: torch.zeros(*s, device=dev)
+    color, radii = rast(means3D=e(0, 3), means2D=e(0, 3), opacities=e(0, 1), colors_precomp=e(0, 32), scales=e(0, 3), rotations=e(0, 4))
+    assert color.shape == (32, 40, 56) and not color.any() and radii.numel() == 0
+    # everything behind the camera: image == background, radii == 0, gradients == 0
+    behind = (c.camera_center[None] * 3.0).repeat(64, 1).to(dev).requires_grad_(True)
+    cols = sc.gauss.colors.to(dev).requires_grad_(True)
+    color, radii = rast(means3D=behind, means2D=e(64, 3), opacities=sc.gauss.opacities.to(dev), colors_precomp=cols,
+                        scales=sc.gauss.scales.to(dev), rotations=sc.gauss.rotations.to(dev))
+    assert not radii.any() and torch.allclose(color.cpu(), bg[:, None, None].expand(32, 40, 56))
+    color.sum().backward()
+    assert not cols.grad.any() and not behind.grad.any()
+    assert not rast.markVisible(behind.detach()).any() and rast.markVisible(sc.gauss.means3D.to(dev)).any()
+    # K != 3 without precomputed colours: the reference's error text
+    rs3 = rs._replace(debug=False)
+    with pytest.raises(RuntimeError, match="For non-RGB, provide precomputed Gaussian colors"):
+        R.GaussianRasterizerContrastiveF(rs3)(means3D=sc.gauss.means3D.to(dev), means2D=e(64, 3), opacities=sc.gauss.opacities.to(dev),
+                                              shs=torch.zeros(64, 16, 3, device=dev), scales=sc.gauss.scales.to(dev),
+                                              rotations=sc.gauss.rotations.to(dev))
+
+
+def test_mask_only_path_matches_depth_variant_mask():
+    from seganygaussians_b200 import rasterizer as R
+    dev = torch.device("cuda", 0)
+    sc = synthetic.scene(3000, 72, 104, 3)
+    g, c = sc.gauss, sc.cam
+    rs = R.GaussianRasterizationSettings(72, 104, c.tanfovx, c.tanfovy, torch.zeros(3, device=dev), 1.0, c.world_view_transform.to(dev),
+                                         c.full_proj_transform.to(dev), 0, c.camera_center.to(dev), False, False)
+    rast = R.GaussianRasterizerDepth(rs)
+    mk = lambda: (torch.rand(3000, 1, generator=torch.Generator().manual_seed(7)) * 0.5 + 0.5).to(dev).requires_grad_(True)
+    m1, m2 = mk(), mk()
+    common_kw = dict(means3D=g.means3D.to(dev), means2D=torch.zeros(3000, 3, device=dev), opacities=g.opacities.to(dev),
+                     scales=g.scales.to(dev), rotations=g.rotations.to(dev))
+    _, out_mask, _, radii = rast(mask=m1, colors_precomp=g.colors.to(dev), **common_kw)
+    mask_only, radii2 = rast.forward_mask(mask=m2, **common_kw)
+    assert torch.equal(out_mask, mask_only) and torch.equal(radii, radii2)
+    gm = sc.dL_dmask.to(dev)
+    (out_mask * gm).sum().backward()
+    (mask_only * gm).sum().backward()
+    assert torch.allclose(m1.grad, m2.grad, rtol=1e-4, atol=1e-9)
