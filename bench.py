@@ -72,7 +72,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -82,13 +82,18 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        """index of the next sample (call at the start / end of the timed region)"""
+        return len(self.rows)
+
+    def stop(self, i0=0, i1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
+        rows = self.rows[i0:(i1 + 1) if i1 is not None else None] or self.rows[-3:]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 6:
                 continue
@@ -232,6 +237,11 @@ def main():
         return float(ms.item())
 
     # ---------------- warm-up, then the timed regions ----------------
+    # the clock sampler starts BEFORE the warm-up (nvidia-smi start-up perturbs the GPU for ~100 ms) and keeps
+    # sampling every 100 ms; only the samples taken during the timed region are reported
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
     for _ in range(max(a.warmup, 3)):
         step_resident()
     step_e2e()
@@ -240,11 +250,9 @@ def main():
         _lib.reset_launch_count()
         _lib.profile_read(reset=True)
         _lib.profile_enable(True)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
+    i0 = sampler.mark() if sampler else 0
     ms_total = timed(step_resident, a.steps)
-    clocks = sampler.stop() if sampler else None
+    i1 = sampler.mark() if sampler else 0
     stage = None
     launches = None
     if a.impl == "ours":
@@ -252,6 +260,7 @@ def main():
         stage = _lib.profile_read(reset=True)
         launches = _lib.launch_count()
     ms_e2e = timed(step_e2e, a.steps)
+    clocks = sampler.stop(i0, i1) if sampler else None
 
     n_used = world if use_dist else 1
     gp_per_step = float(P) * H * W * n_used

@@ -75,7 +75,8 @@ int launch_scan_block_sums(const Dims& d, GeomView g, cudaStream_t s, bool debug
 // each Gaussian its offset (and materialises point_offsets), then every Gaussian writes its tiles.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-duplicate_kernel(int P, const float* __restrict__ geo, const uint32_t* __restrict__ tiles_touched,
+duplicate_kernel(int P, const float* __restrict__ geo, const float* __restrict__ depths,
+                 const uint32_t* __restrict__ tiles_touched,
                  const uint32_t* __restrict__ block_excl, const int32_t* __restrict__ radii,
                  uint32_t* __restrict__ point_offsets, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
                  int tiles_x, int tiles_y)
@@ -102,10 +103,9 @@ duplicate_kernel(int P, const float* __restrict__ geo, const uint32_t* __restric
 
     uint32_t off = incl - n;
     const float4 r0 = *reinterpret_cast<const float4*>(geo + 8 * (size_t)idx);
-    const float4 r1 = *reinterpret_cast<const float4*>(geo + 8 * (size_t)idx + 4);
     uint2 rmin, rmax;
     tile_rect(make_float2(r0.x, r0.y), radii[idx], rmin, rmax, tiles_x, tiles_y);
-    const uint64_t depth_bits = (uint64_t)__float_as_uint(r1.z);
+    const uint64_t depth_bits = (uint64_t)__float_as_uint(depths[idx]);
     for (uint32_t y = rmin.y; y < rmax.y; y++) {
         for (uint32_t x = rmin.x; x < rmax.x; x++) {
             const uint64_t key = ((uint64_t)(y * (uint32_t)tiles_x + x) << 32) | depth_bits;
@@ -120,7 +120,7 @@ int launch_duplicate(const Dims& d, GeomView g, const int32_t* radii, uint64_t* 
                      cudaStream_t s, bool debug)
 {
     const int nblk = (d.P + 255) / 256;
-    duplicate_kernel<<<nblk, 256, 0, s>>>(d.P, g.geo, g.tiles_touched, g.block_sums, radii, g.point_offsets,
+    duplicate_kernel<<<nblk, 256, 0, s>>>(d.P, g.geo, g.depths, g.tiles_touched, g.block_sums, radii, g.point_offsets,
                                           keys, vals, d.tiles_x, d.tiles_y);
     SAGARS_LAUNCH_CHECK(s, debug);
     return SAGARS_OK;

@@ -140,6 +140,34 @@ __device__ __forceinline__ void tile_rect(const float2 p, int max_radius, uint2&
     rmax.y = (unsigned)min(tiles_y, max(0, (int)((p.y + max_radius + SAGARS_TILE_Y - 1) / SAGARS_TILE_Y)));
 }
 
+// Half-extents (in pixels) of an axis-aligned box that contains every pixel centre the blend kernels can
+// accept for this splat, i.e. every d with  power(d) <= 0  and  opacity * exp(power(d)) >= 1/255  where
+// power(d) = -0.5 (cx dx^2 + cz dy^2) - cy dx dy  is evaluated in fp32 from the SAME conic.  The level set
+// {0.5 d^T C d <= t}, t = ln(255 * opacity), has the AABB half-widths sqrt(2 t cz / det C), sqrt(2 t cx / det C).
+// Evaluated in fp64 and inflated (t -> 1.1 t + 0.1, +0.5 px) so that fp32 rounding of `power` in the blend
+// kernels (which grows with the conditioning of C) can never make an accepted pixel fall outside the box.
+// -inf means "no pixel can be accepted" (opacity <= 1/255); +inf means "do not cull".
+// This is purely an acceleration structure: culled (pixel, splat) pairs are exactly pairs the reference
+// skips with `continue` (CF forward.cu:340-349), so results are unchanged.
+__device__ __forceinline__ void cull_extent(const float3& conic, float opacity, float2& ext)
+{
+    const float inf = __int_as_float(0x7f800000);
+    ext = make_float2(inf, inf);
+    if (!(opacity == opacity)) return;              // NaN opacity: never cull
+    if (!(opacity * 255.0f > 1.0f)) {               // alpha = min(.99, o*G) < 1/255 for every G <= 1
+        ext = make_float2(-inf, -inf);           // x + (-inf) >= bx0 is false for every block
+        return;
+    }
+    const double cx = conic.x, cy = conic.y, cz = conic.z;
+    const double det = cx * cz - cy * cy;
+    if (!(det > 0.0) || !(cx > 0.0) || !(cz > 0.0)) return;
+    const double t = 1.1 * log(255.0 * (double)opacity) + 0.1;
+    const double hx = sqrt(2.0 * t * cz / det) + 0.5;
+    const double hy = sqrt(2.0 * t * cx / det) + 0.5;
+    if (!(hx == hx) || !(hy == hy)) return;
+    ext = make_float2(__double2float_ru(hx), __double2float_ru(hy));
+}
+
 // real spherical-harmonics constants (CF auxiliary.h:22-39)
 #define SAGARS_SH_C0 0.28209479177387814f
 #define SAGARS_SH_C1 0.4886025119029199f

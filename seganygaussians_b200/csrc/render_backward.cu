@@ -8,19 +8,20 @@
 //   phase A (thread = pixel, exactly the reference's traversal): recompute alpha, undo T, and reduce
 //     the C-channel work of a pair to ONE dot product s = f_j . g_p.  Because dL/dalpha is linear in
 //     the upstream gradient, the reference's per-channel recurrence accum_rec[ch] collapses to a
-//     scalar recurrence on a = accum_rec . g_p (same association order, Appendix D).  Each blended
-//     pair emits two scalars into shared memory: w = alpha*T (weight of dL/dcolour) and
-//     q = G * dL/dalpha (weight of every geometric gradient), plus a ballot bit.
-//   phase B (thread = (instance, channel quad)): every per-Gaussian gradient is a sparse
-//     matrix product over the tile's pixels,
+//     scalar recurrence on a = accum_rec . g_p (same association order, Appendix D).  A (warp, splat)
+//     pair whose accept box (cull_extent) misses the warp's 8x4 pixel block is skipped with four
+//     warp-uniform compares.  Each blended pair appends (w = alpha*T, q = G*dL/dalpha, pixel) to a
+//     compact per-splat list in shared memory (warp ballot + one shared atomic per (warp, splat)).
+//   phase B (a warp per splat, lane = (list slot, channel quad)): every per-Gaussian gradient is a sparse
+//     product over the tile's pixels,
 //         dL/dcolour[j][:] = sum_p w[j][p] * g[p][:]          (g tile resident in smem, float4 reads)
-//         moments[j][:]    = sum_p q[j][p] * (1, dx, dy, dx^2, dx*dy, dy^2)
-//     accumulated in registers by walking the ballot bits, so there is no cross-lane reduction and no
-//     shared-memory atomic; the six moments give dL/dopacity, dL/dmean2D and dL/dconic in closed form.
+//         moments[j][:]    = sum_p q[j][p] * (1, x, y, x^2, xy, y^2)(p)   (tile-centred pixel coordinates)
+//     accumulated in registers by walking the compact list; the six moments give dL/dopacity, dL/dmean2D
+//     and dL/dconic in closed form.  No per-pair atomics, no cross-lane reduction per pair.
 //   One vectorised `red.global.add.v4.f32` per (tile, Gaussian, channel quad) and six scalar reds per
 //   (tile, Gaussian) then replace the reference's (C+6) x (blended pixels) atomics.
 //
-// Feature rows and instance records are staged with cp.async, double buffered.
+// Instance records are staged with cp.async (double buffered), feature rows with cp.async behind phase B.
 #include "common.cuh"
 #include "cp_async.cuh"
 
@@ -30,45 +31,49 @@ constexpr int BWD_NB = 16;   // instances per batch
 
 template <int NQ>
 struct BwdCfg {
-    static constexpr int TPI = NQ > 8 ? NQ : 8;                 // phase-B threads per instance
-    static constexpr int SPLIT = TILE_PIX / (BWD_NB * TPI);     // pixel-range splits per instance
-    static constexpr int WARPS_PER_SPLIT = 8 / SPLIT;
+    static constexpr int TPI = NQ > 8 ? NQ : 8;   // phase-B lanes per list slot (one per channel quad / moment)
+    static constexpr int SLOTS = 32 / TPI;        // list entries a warp consumes per iteration
 };
 
 template <int NQ>
 struct BwdSmem {
-    float4 Gs[TILE_PIX][NQ];            // upstream gradient rows of the tile's pixels (padded channels = 0)
-    float2 Wq[BWD_NB][TILE_PIX];        // (w, q) per (instance, pixel); valid where the ballot bit is set
-    uint32_t masks[BWD_NB][8];          // ballot of blended pixels per (instance, warp)
-    float4 geo[2][BWD_NB][2];           // x, y, cx, cy | cz, opacity, depth, -
-    float4 feat[2][BWD_NB][NQ];         // feature rows, zero padded
+    float4 Gs[TILE_PIX][NQ];            // upstream gradient rows, indexed by raster-local pixel (y*16 + x); padded channels = 0
+    float2 ent[BWD_NB][TILE_PIX];       // compact list of blended pairs per instance: (w, q)
+    uint8_t entp[BWD_NB][TILE_PIX];     //   ... and their raster-local pixel index
+    uint32_t cnt[2][BWD_NB];            // list lengths (double buffered across batches)
+    float4 geo[2][BWD_NB][2];           // x, y, cx, cy | cz, opacity, cull_hx, cull_hy
+    float4 feat[BWD_NB][NQ];            // feature rows, zero padded
+    float tabx[16][8];                  // moment basis factors in x: 1, x, 1, x^2, x, 1, 0, 0   (x = xl - 7.5)
+    float taby[16][8];                  //                     in y: 1, 1, y, 1, y, y^2, 0, 0
     uint32_t ids[3][BWD_NB];
     uint32_t max_contrib;
 };
 
-template <int NQ, bool VEC>
-__device__ __forceinline__ void bwd_issue_batch(BwdSmem<NQ>& sm, int stage, int idbuf, int cnt, int K,
-                                                const float* __restrict__ geo, const float* __restrict__ features)
+template <int NQ>
+__device__ __forceinline__ void bwd_issue_geo(BwdSmem<NQ>& sm, int stage, int idbuf, int cnt, const float* __restrict__ geo)
 {
     const int tid = threadIdx.x;
     if (tid < cnt * 2) {
         const int j = tid >> 1, h = tid & 1;
-        const uint32_t id = sm.ids[idbuf][j];
-        cp_async16(&sm.geo[stage][j][h], geo + 8 * (size_t)id + 4 * h);
+        cp_async16(&sm.geo[stage][j][h], geo + 8 * (size_t)sm.ids[idbuf][j] + 4 * h);
     }
+}
+
+template <int NQ, bool VEC>
+__device__ __forceinline__ void bwd_issue_feat(BwdSmem<NQ>& sm, int idbuf, int cnt, int K, const float* __restrict__ features)
+{
+    const int tid = threadIdx.x;
     if (VEC) {
         const int nq = K >> 2;
         for (int c = tid; c < cnt * nq; c += TILE_PIX) {
             const int j = c / nq, q = c - j * nq;
-            const uint32_t id = sm.ids[idbuf][j];
-            cp_async16(&sm.feat[stage][j][q], features + (size_t)id * K + 4 * q);
+            cp_async16(&sm.feat[j][q], features + (size_t)sm.ids[idbuf][j] * K + 4 * q);
         }
     } else {
-        float* f = reinterpret_cast<float*>(&sm.feat[stage][0][0]);
+        float* f = reinterpret_cast<float*>(&sm.feat[0][0]);
         for (int c = tid; c < cnt * K; c += TILE_PIX) {
             const int j = c / K, k = c - j * K;
-            const uint32_t id = sm.ids[idbuf][j];
-            f[j * (4 * NQ) + k] = features[(size_t)id * K + k];
+            f[j * (4 * NQ) + k] = features[(size_t)sm.ids[idbuf][j] * K + k];
         }
     }
 }
@@ -76,7 +81,7 @@ __device__ __forceinline__ void bwd_issue_batch(BwdSmem<NQ>& sm, int stage, int 
 // NQ : float4 groups covering the gradient channels (K colour channels [+ 1 mask channel when MD])
 // VEC: K % 4 == 0 and no mask channel -> dL_dcolors rows are 16-byte aligned, use red.v4
 template <int NQ, bool VEC, bool MD, bool COLOR>
-__global__ void __launch_bounds__(TILE_PIX)
+__global__ void __launch_bounds__(TILE_PIX, (NQ <= 8) ? 3 : 1)
 render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                        int W, int H, int K,
                        const float* __restrict__ bg, const float* __restrict__ geo,
@@ -92,12 +97,15 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_x = gridDim.x;
     const uint32_t tile_x0 = blockIdx.x * TILE_X, tile_y0 = blockIdx.y * TILE_Y;
-    const uint32_t px = tile_x0 + (warp & 1) * 8 + (lane & 7);
-    const uint32_t py = tile_y0 + (warp >> 1) * 4 + (lane >> 3);
+    const int xl = (warp & 1) * 8 + (lane & 7), yl = (warp >> 1) * 4 + (lane >> 3);   // this thread's pixel in the tile
+    const int rl = yl * TILE_X + xl;                                                   // raster-local index
+    const uint32_t px = tile_x0 + xl, py = tile_y0 + yl;
     const bool inside = px < (uint32_t)W && py < (uint32_t)H;
     const uint32_t pix_id = (uint32_t)W * py + px;
     const float pixx = (float)px, pixy = (float)py;
     const size_t plane = (size_t)H * W;
+    const float bx0 = (float)(tile_x0 + (warp & 1) * 8), bx1 = bx0 + 7.f;
+    const float by0 = (float)(tile_y0 + (warp >> 1) * 4), by1 = by0 + 3.f;
 
     const uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];
     const int total = (int)(range.y - range.x);
@@ -105,15 +113,20 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     const float T_final = inside ? final_Ts[pix_id] : 0.f;
     const int my_n = inside ? (int)n_contrib[pix_id] : 0;
 
-    // the tile only needs instances [0, max over its pixels of n_contrib)
+    // the tile only needs instances [0, max over its pixels of n_contrib); a warp only [0, its own max)
     if (tid == 0) sm.max_contrib = 0;
-    __syncthreads();
-    {
-        int m = my_n;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0 && m > 0) atomicMax(&sm.max_contrib, (uint32_t)m);
+    if (tid < 2 * BWD_NB) sm.cnt[tid / BWD_NB][tid % BWD_NB] = 0;
+    if (tid < 128) {   // moment basis tables
+        const int c = tid >> 3, k = tid & 7;
+        const float v = (float)c - 7.5f;
+        sm.tabx[c][k] = (k == 1 || k == 4) ? v : (k == 3) ? v * v : (k <= 5) ? 1.f : 0.f;
+        sm.taby[c][k] = (k == 2 || k == 4) ? v : (k == 5) ? v * v : (k <= 5) ? 1.f : 0.f;
     }
+    __syncthreads();
+    int warp_n = my_n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) warp_n = max(warp_n, __shfl_xor_sync(0xffffffffu, warp_n, o));
+    if (lane == 0 && warp_n > 0) atomicMax(&sm.max_contrib, (uint32_t)warp_n);
 
     // upstream gradient of this pixel: registers for phase A, smem row for phase B
     float g[4 * NQ];
@@ -138,12 +151,12 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
             if (K == 4 * q + 2) v.z = gmask;
             if (K == 4 * q + 3) v.w = gmask;
         }
-        sm.Gs[tid][q] = v;
+        sm.Gs[rl][q] = v;
     }
     // zero the padded feature channels once
     if (!VEC || (K >> 2) < NQ) {
-        float* f = reinterpret_cast<float*>(&sm.feat[0][0][0]);
-        for (int c = tid; c < 2 * BWD_NB * 4 * NQ; c += TILE_PIX) f[c] = 0.f;
+        float* f = reinterpret_cast<float*>(&sm.feat[0][0]);
+        for (int c = tid; c < BWD_NB * 4 * NQ; c += TILE_PIX) f[c] = 0.f;
     }
     __syncthreads();
 
@@ -157,7 +170,8 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     // prologue
     if (tid < batch_cnt(0)) sm.ids[0][tid] = load_id(0, tid);
     __syncthreads();
-    bwd_issue_batch<NQ, VEC>(sm, 0, 0, batch_cnt(0), K, geo, features);
+    bwd_issue_geo<NQ>(sm, 0, 0, batch_cnt(0), geo);
+    if (COLOR) bwd_issue_feat<NQ, VEC>(sm, 0, batch_cnt(0), K, features);
     cp_async_commit();
     if (nbatch > 1 && tid < batch_cnt(1)) sm.ids[1][tid] = load_id(1, tid);
     cp_async_wait_all();
@@ -166,18 +180,12 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     float T = T_final;
     float acc = 0.f, last_alpha = 0.f, last_s = 0.f;
 
-    // phase-B role of this thread
-    const int b_split = tid / (BWD_NB * Cfg::TPI);
-    const int b_jj = (tid % (BWD_NB * Cfg::TPI)) / Cfg::TPI;
-    const int b_k = tid % Cfg::TPI;
-    // moment basis of lane k: (a0 + a1 dx + a2 dy) * (b0 + b1 dx + b2 dy)
-    const float ma0 = (b_k == 0) ? 1.f : 0.f;
-    const float ma1 = (b_k == 1 || b_k == 3 || b_k == 4) ? 1.f : 0.f;
-    const float ma2 = (b_k == 2 || b_k == 5) ? 1.f : 0.f;
-    const float mb0 = (b_k <= 2) ? 1.f : 0.f;
-    const float mb1 = (b_k == 3) ? 1.f : 0.f;
-    const float mb2 = (b_k == 4 || b_k == 5) ? 1.f : 0.f;
+    // phase-B role of this lane
+    const int b_slot = lane / Cfg::TPI;
+    const int b_k = lane % Cfg::TPI;
     const float half_W = 0.5f * (float)W, half_H = 0.5f * (float)H;   // (0.5 * W) rounded to float, as the reference
+    const float tcx = (float)tile_x0 + 7.5f, tcy = (float)tile_y0 + 7.5f;
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
     for (int b = 0; b < nbatch; b++) {
         const int stage = b & 1;
@@ -185,96 +193,113 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
         const int cnt = batch_cnt(b);
         const int pos_hi = maxc - 1 - b * BWD_NB;
 
-        // (A) copies of batch b+1, (B) ids of batch b+2
+        // records of batch b+1 start flying; ids of batch b+2 into a register; next batch's list lengths cleared
         if (b + 1 < nbatch) {
-            bwd_issue_batch<NQ, VEC>(sm, stage ^ 1, (b + 1) % 3, batch_cnt(b + 1), K, geo, features);
+            bwd_issue_geo<NQ>(sm, stage ^ 1, (b + 1) % 3, batch_cnt(b + 1), geo);
             cp_async_commit();
         }
         uint32_t next_id = 0;
         const bool have_next_id = (b + 2 < nbatch) && tid < batch_cnt(b + 2);
         if (have_next_id) next_id = load_id(b + 2, tid);
+        if (tid < BWD_NB) sm.cnt[stage ^ 1][tid] = 0;
 
         // ---------------- phase A: thread = pixel ----------------
-        for (int jj = 0; jj < cnt; jj++) {
-            bool blended = false;
-            if (pos_hi - jj < my_n) {
+        if (pos_hi - (cnt - 1) < warp_n) {   // some pixel of this warp still has contributors in this batch
+            for (int jj = 0; jj < cnt; jj++) {
+                if (pos_hi - jj >= warp_n) continue;                                    // warp-uniform
                 const float4 g0 = sm.geo[stage][jj][0];
                 const float4 g1 = sm.geo[stage][jj][1];
-                const float dx = g0.x - pixx, dy = g0.y - pixy;
-                const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
-                if (!(power > 0.0f)) {
-                    const float G = expf(power);
-                    const float alpha = fminf(0.99f, g1.y * G);
-                    if (!(alpha < 1.0f / 255.0f)) {
-                        T = T / (1.f - alpha);
-                        const float w = alpha * T;
-                        float s = 0.f;
-                        if (COLOR) {
+                const bool hit = (g0.x + g1.z >= bx0) && (g0.x - g1.z <= bx1) && (g0.y + g1.w >= by0) && (g0.y - g1.w <= by1);
+                if (!hit) continue;                                                     // warp-uniform
+                bool blended = false;
+                float w_out = 0.f, q_out = 0.f;
+                if (pos_hi - jj < my_n) {
+                    const float dx = g0.x - pixx, dy = g0.y - pixy;
+                    const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
+                    if (!(power > 0.0f)) {
+                        const float G = expf(power);
+                        const float alpha = fminf(0.99f, g1.y * G);
+                        if (!(alpha < 1.0f / 255.0f)) {
+                            T = T / (1.f - alpha);
+                            w_out = alpha * T;
+                            float s = 0.f;
+                            if (COLOR) {
 #pragma unroll
-                            for (int q = 0; q < NQ; q++) {
-                                const float4 f = sm.feat[stage][jj][q];
-                                s += f.x * g[4 * q + 0];
-                                s += f.y * g[4 * q + 1];
-                                s += f.z * g[4 * q + 2];
-                                s += f.w * g[4 * q + 3];
+                                for (int q = 0; q < NQ; q++) {
+                                    const float4 f = sm.feat[jj][q];
+                                    s += f.x * g[4 * q + 0];
+                                    s += f.y * g[4 * q + 1];
+                                    s += f.z * g[4 * q + 2];
+                                    s += f.w * g[4 * q + 3];
+                                }
                             }
+                            acc = last_alpha * last_s + (1.f - last_alpha) * acc;
+                            last_s = s;
+                            float dL_dalpha = (s - acc) * T;
+                            last_alpha = alpha;
+                            dL_dalpha += (-T_final / (1.f - alpha)) * bgdot;
+                            q_out = G * dL_dalpha;
+                            blended = true;
                         }
-                        acc = last_alpha * last_s + (1.f - last_alpha) * acc;
-                        last_s = s;
-                        float dL_dalpha = (s - acc) * T;
-                        last_alpha = alpha;
-                        dL_dalpha += (-T_final / (1.f - alpha)) * bgdot;
-                        sm.Wq[jj][tid] = make_float2(w, G * dL_dalpha);
-                        blended = true;
+                    }
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, blended);
+                if (m != 0u) {
+                    const int leader = __ffs(m) - 1;
+                    uint32_t base = 0;
+                    if (lane == leader) base = atomicAdd(&sm.cnt[stage][jj], (uint32_t)__popc(m));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (blended) {
+                        const uint32_t e = base + __popc(m & lt_mask);
+                        sm.ent[jj][e] = make_float2(w_out, q_out);
+                        sm.entp[jj][e] = (uint8_t)rl;
                     }
                 }
             }
-            const uint32_t m = __ballot_sync(0xffffffffu, blended);
-            if (lane == 0) sm.masks[jj][warp] = m;
         }
         __syncthreads();
 
-        // ---------------- phase B: thread = (instance, channel quad / moment) ----------------
-        {
-            const bool active = b_jj < cnt;
+        // feature rows of batch b+1 (the single feature buffer is free now)
+        if (COLOR && b + 1 < nbatch) {
+            bwd_issue_feat<NQ, VEC>(sm, (b + 1) % 3, batch_cnt(b + 1), K, features);
+            cp_async_commit();
+        }
+
+        // ---------------- phase B: a warp per instance, lane = (list slot, channel quad / moment) ----------------
+        for (int jj = warp; jj < cnt; jj += 8) {
+            const int n = (int)sm.cnt[stage][jj];
+            if (n == 0) continue;                                                       // warp-uniform
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
             float mom = 0.f;
-            uint32_t any = 0;
-            float xg = 0.f, yg = 0.f;
-            if (active) {
-                const float4 g0 = sm.geo[stage][b_jj][0];
-                xg = g0.x;
-                yg = g0.y;
-#pragma unroll
-                for (int wi = 0; wi < Cfg::WARPS_PER_SPLIT; wi++) {
-                    const int wrp = b_split * Cfg::WARPS_PER_SPLIT + wi;
-                    uint32_t m = sm.masks[b_jj][wrp];
-                    any |= m;
-                    const float wx = (float)(tile_x0 + (wrp & 1) * 8);
-                    const float wy = (float)(tile_y0 + (wrp >> 1) * 4);
-                    while (m) {
-                        const int l = __ffs(m) - 1;
-                        m &= m - 1;
-                        const int p = wrp * 32 + l;
-                        const float2 wq = sm.Wq[b_jj][p];
-                        if (b_k < NQ) {
-                            const float4 gv = sm.Gs[p][b_k < NQ ? b_k : 0];
-                            a.x += wq.x * gv.x;
-                            a.y += wq.x * gv.y;
-                            a.z += wq.x * gv.z;
-                            a.w += wq.x * gv.w;
-                        }
-                        const float dx = xg - (wx + (float)(l & 7));
-                        const float dy = yg - (wy + (float)(l >> 3));
-                        mom += wq.y * ((ma0 + ma1 * dx + ma2 * dy) * (mb0 + mb1 * dx + mb2 * dy));
-                    }
+            for (int i = b_slot; i < n; i += Cfg::SLOTS) {
+                const float2 wq = sm.ent[jj][i];
+                const int p = sm.entp[jj][i];
+                if (b_k < NQ) {
+                    const float4 gv = sm.Gs[p][b_k < NQ ? b_k : 0];
+                    a.x += wq.x * gv.x;
+                    a.y += wq.x * gv.y;
+                    a.z += wq.x * gv.z;
+                    a.w += wq.x * gv.w;
                 }
+                if (b_k < 8) mom += wq.y * (sm.tabx[p & 15][b_k] * sm.taby[p >> 4][b_k]);
             }
-            // moments of lanes 1 and 2 of this instance's lane group (dmean needs both)
-            const float m1 = __shfl_sync(0xffffffffu, mom, 1, Cfg::TPI);
-            const float m2 = __shfl_sync(0xffffffffu, mom, 2, Cfg::TPI);
-            if (active && any) {
-                const uint32_t id = sm.ids[idb][b_jj];
+#pragma unroll
+            for (int o = Cfg::TPI; o < 32; o <<= 1) {
+                a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+                a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+                a.z += __shfl_xor_sync(0xffffffffu, a.z, o);
+                a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+                mom += __shfl_xor_sync(0xffffffffu, mom, o);
+            }
+            // raw moments about the tile centre (lanes 0..5 of every slot group hold m0, mx, my, mxx, mxy, myy)
+            const float m0 = __shfl_sync(0xffffffffu, mom, 0, Cfg::TPI);
+            const float mx = __shfl_sync(0xffffffffu, mom, 1, Cfg::TPI);
+            const float my = __shfl_sync(0xffffffffu, mom, 2, Cfg::TPI);
+            const float mxx = __shfl_sync(0xffffffffu, mom, 3, Cfg::TPI);
+            const float mxy = __shfl_sync(0xffffffffu, mom, 4, Cfg::TPI);
+            const float myy = __shfl_sync(0xffffffffu, mom, 5, Cfg::TPI);
+            if (b_slot == 0) {
+                const uint32_t id = sm.ids[idb][jj];
                 if (b_k < NQ) {
                     if (VEC) {
                         if (4 * b_k < K) red_add_v4(dL_dcolors + (size_t)id * K + 4 * b_k, a.x, a.y, a.z, a.w);
@@ -289,21 +314,30 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
                     }
                 }
                 if (b_k < 6) {
-                    const float4 g0 = sm.geo[stage][b_jj][0];
-                    const float4 g1 = sm.geo[stage][b_jj][1];
-                    const float cx = g0.z, cy = g0.w, cz = g1.x, o = g1.y;
+                    const float4 g0 = sm.geo[stage][jj][0];
+                    const float4 g1 = sm.geo[stage][jj][1];
+                    const float conx = g0.z, cony = g0.w, conz = g1.x, o = g1.y;
+                    // sums over the pixels of q * (1, dx, dy, dx^2, dx dy, dy^2) with d = centre - pixel = c - x'
+                    const float cx = g0.x - tcx, cy = g0.y - tcy;
+                    const float Sx = cx * m0 - mx;
+                    const float Sy = cy * m0 - my;
+                    const float Sxx = cx * cx * m0 - 2.f * cx * mx + mxx;
+                    const float Sxy = cx * cy * m0 - cx * my - cy * mx + mxy;
+                    const float Syy = cy * cy * m0 - 2.f * cy * my + myy;
                     float v;
                     int slot;
-                    if (b_k == 0) { v = mom; slot = 5; }                                          // dL/dopacity
-                    else if (b_k == 1) { v = -o * half_W * (cx * m1 + cy * m2); slot = 0; }       // dL/dmean2D.x
-                    else if (b_k == 2) { v = -o * half_H * (cz * m2 + cy * m1); slot = 1; }       // dL/dmean2D.y
-                    else { v = -0.5f * o * mom; slot = b_k - 1; }                                 // dL/dconic x,y,w
+                    if (b_k == 0) { v = m0; slot = 5; }                                           // dL/dopacity
+                    else if (b_k == 1) { v = -o * half_W * (conx * Sx + cony * Sy); slot = 0; }   // dL/dmean2D.x
+                    else if (b_k == 2) { v = -o * half_H * (conz * Sy + cony * Sx); slot = 1; }   // dL/dmean2D.y
+                    else if (b_k == 3) { v = -0.5f * o * Sxx; slot = 2; }                         // dL/dconic.x
+                    else if (b_k == 4) { v = -0.5f * o * Sxy; slot = 3; }                         // dL/dconic.y
+                    else { v = -0.5f * o * Syy; slot = 4; }                                       // dL/dconic.w
                     red_add(ggrad + (size_t)id * GG_STRIDE + slot, v);
                 }
             }
         }
 
-        // (D) publish ids(b+2); wait for the copies of batch b+1
+        // publish ids(b+2); wait for the copies of batch b+1
         if (have_next_id) sm.ids[(b + 2) % 3][tid] = next_id;
         cp_async_wait_all();
         __syncthreads();

@@ -12,6 +12,8 @@
 //     (warp, Gaussian) pairs that have any pixel to blend;
 //   * a warp stops as soon as its 32 pixels are saturated (the reference only stops per CTA, per
 //     256-instance batch);
+//   * every (warp, splat) pair whose accept box misses the warp's pixel block is rejected with four
+//     warp-uniform compares (the box is a superset of the pixels the reference's tests accept);
 //   * C is a run-time value (<= 64), dispatched onto float4-group templates.
 // The per-pixel arithmetic (power, alpha, the 1/255 and 1e-4 tests, the order of accumulation)
 // is kept operation for operation so that n_contrib / final_T / colours match the reference.
@@ -24,17 +26,18 @@ constexpr int FWD_BATCH = 64;   // instances staged per pipeline stage
 
 template <int NQ>
 struct FwdSmem {
-    float4 geo[2][FWD_BATCH][2];        // x, y, cx, cy | cz, opacity, depth, -
+    float4 geo[2][FWD_BATCH][2];        // x, y, cx, cy | cz, opacity, cull_hx, cull_hy
     float4 feat[2][FWD_BATCH][NQ];      // feature rows, zero padded to 4*NQ channels
     uint32_t ids[2][FWD_BATCH];
     float maskv[2][FWD_BATCH];          // DEPTH variant: per-instance mask value
+    float depthv[2][FWD_BATCH];         // DEPTH variant: per-instance view depth
 };
 
 // issue the asynchronous copies of one batch (ids already in smem)
 template <int NQ, bool VEC, bool MD, bool COLOR>
 __device__ __forceinline__ void fwd_issue_batch(FwdSmem<NQ>& sm, int stage, int idbuf, int cnt, int K,
                                                 const float* __restrict__ geo, const float* __restrict__ features,
-                                                const float* __restrict__ mask)
+                                                const float* __restrict__ mask, const float* __restrict__ depths)
 {
     const int tid = threadIdx.x;
     // geometry records: 2 x 16 B per instance
@@ -44,7 +47,11 @@ __device__ __forceinline__ void fwd_issue_batch(FwdSmem<NQ>& sm, int stage, int 
         cp_async16(&sm.geo[stage][j][h], geo + 8 * (size_t)id + 4 * h);
     }
     if (MD) {
-        if (tid < cnt) sm.maskv[stage][tid] = mask[sm.ids[idbuf][tid]];
+        if (tid < cnt) {
+            const uint32_t id = sm.ids[idbuf][tid];
+            sm.maskv[stage][tid] = mask[id];
+            sm.depthv[stage][tid] = depths[id];
+        }
     }
     if (!COLOR) return;
     if (VEC) {
@@ -69,7 +76,7 @@ __global__ void __launch_bounds__(TILE_PIX)
 render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                       int W, int H, int K,
                       const float* __restrict__ geo, const float* __restrict__ features,
-                      const float* __restrict__ mask, const float* __restrict__ bg,
+                      const float* __restrict__ mask, const float* __restrict__ depths, const float* __restrict__ bg,
                       float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
                       float* __restrict__ out_color, float* __restrict__ out_mask, float* __restrict__ out_depth)
 {
@@ -83,6 +90,10 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     const bool inside = px < (uint32_t)W && py < (uint32_t)H;
     const uint32_t pix_id = (uint32_t)W * py + px;
     const float pixx = (float)px, pixy = (float)py;
+    // pixel-centre bounds of this warp's 8x4 block (warp-uniform): a splat whose accept box (cull_extent)
+    // misses the block is skipped by every lane of the warp with four compares
+    const float bx0 = (float)(blockIdx.x * TILE_X + (warp & 1) * 8), bx1 = bx0 + 7.f;
+    const float by0 = (float)(blockIdx.y * TILE_Y + (warp >> 1) * 4), by1 = by0 + 3.f;
 
     const uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];
     const int total = (int)(range.y - range.x);
@@ -106,7 +117,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     if (nbatch > 0) {
         if (tid < min(FWD_BATCH, total)) sm.ids[0][tid] = point_list[range.x + tid];
         __syncthreads();
-        fwd_issue_batch<NQ, VEC, MD, COLOR>(sm, 0, 0, min(FWD_BATCH, total), K, geo, features, mask);
+        fwd_issue_batch<NQ, VEC, MD, COLOR>(sm, 0, 0, min(FWD_BATCH, total), K, geo, features, mask, depths);
         cp_async_commit();
         if (nbatch > 1 && tid < min(FWD_BATCH, total - FWD_BATCH)) sm.ids[1][tid] = point_list[range.x + FWD_BATCH + tid];
         cp_async_wait_all();
@@ -122,7 +133,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         // (A) start the copies of batch b+1 (its ids were stored one iteration ago)
         if (b + 1 < nbatch) {
             fwd_issue_batch<NQ, VEC, MD, COLOR>(sm, stage ^ 1, (b + 1) & 1, min(FWD_BATCH, total - (b + 1) * FWD_BATCH),
-                                         K, geo, features, mask);
+                                         K, geo, features, mask, depths);
             cp_async_commit();
         }
         // (B) ids of batch b+2 into a register
@@ -134,9 +145,11 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         // (C) blend batch b
         if (!__all_sync(0xffffffffu, done)) {
             for (int j = 0; j < cnt; j++) {
-                if (!done) {
-                    const float4 g0 = sm.geo[stage][j][0];
-                    const float4 g1 = sm.geo[stage][j][1];
+                const float4 g0 = sm.geo[stage][j][0];
+                const float4 g1 = sm.geo[stage][j][1];
+                // warp-uniform reject: (g1.z, g1.w) = half extents of the splat's accept box
+                const bool hit = (g0.x + g1.z >= bx0) && (g0.x - g1.z <= bx1) && (g0.y + g1.w >= by0) && (g0.y - g1.w <= by1);
+                if (hit && !done) {
                     const float dx = g0.x - pixx, dy = g0.y - pixy;
                     const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
                     if (!(power > 0.0f)) {
@@ -158,7 +171,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                                 }
                                 if (MD) {
                                     Macc += sm.maskv[stage][j] * alpha * T;
-                                    Dacc += g1.z * alpha * T;
+                                    Dacc += sm.depthv[stage][j] * alpha * T;
                                 }
                                 T = test_T;
                                 last_contributor = (uint32_t)(b * FWD_BATCH + j + 1);
@@ -200,7 +213,7 @@ static int launch_fwd_t(const sagars_forward_args& a, const Dims& d, GeomView g,
     const size_t smem = sizeof(FwdSmem<NQ>);
     SAGARS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(d.tiles_x, d.tiles_y);
-    kern<<<grid, TILE_PIX, smem, s>>>(im.ranges, point_list, d.W, d.H, d.C, g.geo, features, a.mask, a.background,
+    kern<<<grid, TILE_PIX, smem, s>>>(im.ranges, point_list, d.W, d.H, d.C, g.geo, features, a.mask, g.depths, a.background,
                                       im.final_T, im.n_contrib, a.out_color, a.out_mask, a.out_depth);
     SAGARS_LAUNCH_CHECK(s, debug);
     return SAGARS_OK;

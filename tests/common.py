@@ -157,7 +157,8 @@ def _decode(o, kind, sc, geom, binning, img):
         o.tiles_touched = _bytes_view(geom, gl.tiles_touched, np.uint32, P)
         o.point_offsets = _bytes_view(geom, gl.point_offsets, np.uint32, P)
         geo = _bytes_view(geom, gl.geo, np.float32, P * 8).reshape(P, 8)
-        o.means2D, o.conic_opacity, o.depths = geo[:, 0:2].copy(), geo[:, 2:6].copy(), geo[:, 6].copy()
+        o.means2D, o.conic_opacity = geo[:, 0:2].copy(), geo[:, 2:6].copy()
+        o.depths = _bytes_view(geom, gl.depths, np.float32, P)
         o.cov3D = _bytes_view(geom, gl.cov3D, np.float32, P * 6).reshape(P, 6)
         o.final_T = _bytes_view(img, il.final_T, np.float32, N).reshape(H, W)
         o.n_contrib = _bytes_view(img, il.n_contrib, np.uint32, N).reshape(H, W)
