@@ -177,7 +177,7 @@ SAGARS_API size_t sagars_grad_scratch_bytes(int32_t P);
  * BinningState (CF rasterizer_impl.cu:155-194).  The layout is otherwise private. */
 typedef struct sagars_geom_layout {
     size_t depths;          /* f32[P]   view-space z                                                 */
-    size_t geo;             /* f32[P,8] {x, y, conic.x, conic.y, conic.z, opacity, cull_hx, cull_hy}         */
+    size_t geo;             /* f32[P,8] {x, y, conic.x, conic.y, conic.z, opacity, accept_threshold, 0}         */
     size_t cov3D;           /* f32[P,6]                                                              */
     size_t rgb;             /* f32[P,3] SH->RGB result (only when shs given)                         */
     size_t clamped;         /* u8[P,3]                                                               */

@@ -25,7 +25,7 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a = 256) { return (x
 
 struct GeomView {
     float* depths;            // [P]
-    float* geo;               // [P][8]  x, y, conic.x, conic.y, conic.z, opacity, cull_hx, cull_hy
+    float* geo;               // [P][8]  x, y, conic.x, conic.y, conic.z, opacity, accept_threshold, 0
     float* cov3D;             // [P][6]
     float* rgb;               // [P][3]
     uint8_t* clamped;         // [P][3]

@@ -140,32 +140,22 @@ __device__ __forceinline__ void tile_rect(const float2 p, int max_radius, uint2&
     rmax.y = (unsigned)min(tiles_y, max(0, (int)((p.y + max_radius + SAGARS_TILE_Y - 1) / SAGARS_TILE_Y)));
 }
 
-// Half-extents (in pixels) of an axis-aligned box that contains every pixel centre the blend kernels can
-// accept for this splat, i.e. every d with  power(d) <= 0  and  opacity * exp(power(d)) >= 1/255  where
-// power(d) = -0.5 (cx dx^2 + cz dy^2) - cy dx dy  is evaluated in fp32 from the SAME conic.  The level set
-// {0.5 d^T C d <= t}, t = ln(255 * opacity), has the AABB half-widths sqrt(2 t cz / det C), sqrt(2 t cx / det C).
-// Evaluated in fp64 and inflated (t -> 1.1 t + 0.1, +0.5 px) so that fp32 rounding of `power` in the blend
-// kernels (which grows with the conditioning of C) can never make an accepted pixel fall outside the box.
-// -inf means "no pixel can be accepted" (opacity <= 1/255); +inf means "do not cull".
-// This is purely an acceleration structure: culled (pixel, splat) pairs are exactly pairs the reference
-// skips with `continue` (CF forward.cu:340-349), so results are unchanged.
-__device__ __forceinline__ void cull_extent(const float3& conic, float opacity, float2& ext)
+// Conservative lower bound on `power` below which a (pixel, splat) pair is certainly rejected by the blend
+// kernels' exact test  alpha = min(0.99, opacity * expf(power)) >= 1/255 :
+//     opacity * exp(power) >= 1/255   <=>   power >= -ln(255 * opacity),
+// so any pair with power < -ln(255*opacity) - margin is skipped without evaluating expf.  The margin (1e-4
+// absolute + 1e-5 relative) dwarfs the error of logf here and of expf / the product rounding there (~1e-6), and the
+// blend kernels compare the SAME fp32 `power` value they would exponentiate, so no conditioning enters.
+// +inf = the splat can never be accepted (opacity <= 1/255); -inf = never skip (NaN opacity).
+// This is purely an acceleration structure: skipped pairs are exactly pairs the reference skips with
+// `continue` (CF forward.cu:340-349), so results are unchanged.
+__device__ __forceinline__ float accept_threshold(float opacity)
 {
     const float inf = __int_as_float(0x7f800000);
-    ext = make_float2(inf, inf);
-    if (!(opacity == opacity)) return;              // NaN opacity: never cull
-    if (!(opacity * 255.0f > 1.0f)) {               // alpha = min(.99, o*G) < 1/255 for every G <= 1
-        ext = make_float2(-inf, -inf);           // x + (-inf) >= bx0 is false for every block
-        return;
-    }
-    const double cx = conic.x, cy = conic.y, cz = conic.z;
-    const double det = cx * cz - cy * cy;
-    if (!(det > 0.0) || !(cx > 0.0) || !(cz > 0.0)) return;
-    const double t = 1.1 * log(255.0 * (double)opacity) + 0.1;
-    const double hx = sqrt(2.0 * t * cz / det) + 0.5;
-    const double hy = sqrt(2.0 * t * cx / det) + 0.5;
-    if (!(hx == hx) || !(hy == hy)) return;
-    ext = make_float2(__double2float_ru(hx), __double2float_ru(hy));
+    if (!(opacity == opacity)) return -inf;
+    if (!(opacity * 255.0f > 1.0f)) return inf;
+    const float t = logf(255.0f * opacity);          // > 0
+    return -(t + 1e-5f * t + 1e-4f);
 }
 
 // real spherical-harmonics constants (CF auxiliary.h:22-39)

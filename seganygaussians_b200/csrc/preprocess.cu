@@ -95,11 +95,9 @@ preprocess_kernel(int P, int D, int M, int C,
 
             g.depths[idx] = p_view.z;
             const float opac = opacities[idx];
-            float2 ext;
-            cull_extent(conic, opac, ext);
             float4* rec = reinterpret_cast<float4*>(g.geo + 8 * (size_t)idx);
             rec[0] = make_float4(pix.x, pix.y, conic.x, conic.y);
-            rec[1] = make_float4(conic.z, opac, ext.x, ext.y);
+            rec[1] = make_float4(conic.z, opac, accept_threshold(opac), 0.f);
             my_radius_i = (int)my_radius;
             my_tiles = ntiles;
         } while (false);

@@ -9,8 +9,8 @@
 //     the C-channel work of a pair to ONE dot product s = f_j . g_p.  Because dL/dalpha is linear in
 //     the upstream gradient, the reference's per-channel recurrence accum_rec[ch] collapses to a
 //     scalar recurrence on a = accum_rec . g_p (same association order, Appendix D).  A (warp, splat)
-//     pair whose accept box (cull_extent) misses the warp's 8x4 pixel block is skipped with four
-//     warp-uniform compares.  Each blended pair appends (w = alpha*T, q = G*dL/dalpha, pixel) to a
+//     pair in which no pixel can pass the reference's tests (conservative lower bound on `power`, see
+//     accept_threshold) is skipped with one warp vote before expf.  Each blended pair appends (w = alpha*T, q = G*dL/dalpha, pixel) to a
 //     compact per-splat list in shared memory (warp ballot + one shared atomic per (warp, splat)).
 //   phase B (a warp per splat, lane = (list slot, channel quad)): every per-Gaussian gradient is a sparse
 //     product over the tile's pixels,
@@ -41,7 +41,7 @@ struct BwdSmem {
     float2 ent[BWD_NB][TILE_PIX];       // compact list of blended pairs per instance: (w, q)
     uint8_t entp[BWD_NB][TILE_PIX];     //   ... and their raster-local pixel index
     uint32_t cnt[2][BWD_NB];            // list lengths (double buffered across batches)
-    float4 geo[2][BWD_NB][2];           // x, y, cx, cy | cz, opacity, cull_hx, cull_hy
+    float4 geo[2][BWD_NB][2];           // x, y, cx, cy | cz, opacity, accept_threshold, -
     float4 feat[BWD_NB][NQ];            // feature rows, zero padded
     float tabx[16][8];                  // moment basis factors in x: 1, x, 1, x^2, x, 1, 0, 0   (x = xl - 7.5)
     float taby[16][8];                  //                     in y: 1, 1, y, 1, y, y^2, 0, 0
@@ -104,8 +104,6 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     const uint32_t pix_id = (uint32_t)W * py + px;
     const float pixx = (float)px, pixy = (float)py;
     const size_t plane = (size_t)H * W;
-    const float bx0 = (float)(tile_x0 + (warp & 1) * 8), bx1 = bx0 + 7.f;
-    const float by0 = (float)(tile_y0 + (warp >> 1) * 4), by1 = by0 + 3.f;
 
     const uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];
     const int total = (int)(range.y - range.x);
@@ -209,38 +207,39 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
                 if (pos_hi - jj >= warp_n) continue;                                    // warp-uniform
                 const float4 g0 = sm.geo[stage][jj][0];
                 const float4 g1 = sm.geo[stage][jj][1];
-                const bool hit = (g0.x + g1.z >= bx0) && (g0.x - g1.z <= bx1) && (g0.y + g1.w >= by0) && (g0.y - g1.w <= by1);
-                if (!hit) continue;                                                     // warp-uniform
+                const float dx = g0.x - pixx, dy = g0.y - pixy;
+                const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
+                // g1.z = accept_threshold(opacity); one vote rejects the splat for the whole warp before expf
+                const bool cand = (pos_hi - jj < my_n) && !(power > 0.0f) && (power >= g1.z);
+                if (!__any_sync(0xffffffffu, cand)) continue;                           // warp-uniform
                 bool blended = false;
                 float w_out = 0.f, q_out = 0.f;
-                if (pos_hi - jj < my_n) {
-                    const float dx = g0.x - pixx, dy = g0.y - pixy;
-                    const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
-                    if (!(power > 0.0f)) {
-                        const float G = expf(power);
-                        const float alpha = fminf(0.99f, g1.y * G);
-                        if (!(alpha < 1.0f / 255.0f)) {
-                            T = T / (1.f - alpha);
-                            w_out = alpha * T;
-                            float s = 0.f;
-                            if (COLOR) {
+                if (cand) {
+                    const float G = expf(power);
+                    const float alpha = fminf(0.99f, g1.y * G);
+                    if (!(alpha < 1.0f / 255.0f)) {
+                        T = T / (1.f - alpha);
+                        w_out = alpha * T;
+                        float s = 0.f;
+                        if (COLOR) {
+                            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four chains instead of one 4*NQ-long one
 #pragma unroll
-                                for (int q = 0; q < NQ; q++) {
-                                    const float4 f = sm.feat[jj][q];
-                                    s += f.x * g[4 * q + 0];
-                                    s += f.y * g[4 * q + 1];
-                                    s += f.z * g[4 * q + 2];
-                                    s += f.w * g[4 * q + 3];
-                                }
+                            for (int q = 0; q < NQ; q++) {
+                                const float4 f = sm.feat[jj][q];
+                                s0 += f.x * g[4 * q + 0];
+                                s1 += f.y * g[4 * q + 1];
+                                s2 += f.z * g[4 * q + 2];
+                                s3 += f.w * g[4 * q + 3];
                             }
-                            acc = last_alpha * last_s + (1.f - last_alpha) * acc;
-                            last_s = s;
-                            float dL_dalpha = (s - acc) * T;
-                            last_alpha = alpha;
-                            dL_dalpha += (-T_final / (1.f - alpha)) * bgdot;
-                            q_out = G * dL_dalpha;
-                            blended = true;
+                            s = (s0 + s1) + (s2 + s3);
                         }
+                        acc = last_alpha * last_s + (1.f - last_alpha) * acc;
+                        last_s = s;
+                        float dL_dalpha = (s - acc) * T;
+                        last_alpha = alpha;
+                        dL_dalpha += (-T_final / (1.f - alpha)) * bgdot;
+                        q_out = G * dL_dalpha;
+                        blended = true;
                     }
                 }
                 const uint32_t m = __ballot_sync(0xffffffffu, blended);

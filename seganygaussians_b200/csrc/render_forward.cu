@@ -12,8 +12,8 @@
 //     (warp, Gaussian) pairs that have any pixel to blend;
 //   * a warp stops as soon as its 32 pixels are saturated (the reference only stops per CTA, per
 //     256-instance batch);
-//   * every (warp, splat) pair whose accept box misses the warp's pixel block is rejected with four
-//     warp-uniform compares (the box is a superset of the pixels the reference's tests accept);
+//   * a (warp, splat) pair in which no pixel can pass the reference's tests (power <= 0 and a conservative
+//     per-splat lower bound on power that implies alpha >= 1/255) is rejected with one warp vote, before expf;
 //   * C is a run-time value (<= 64), dispatched onto float4-group templates.
 // The per-pixel arithmetic (power, alpha, the 1/255 and 1e-4 tests, the order of accumulation)
 // is kept operation for operation so that n_contrib / final_T / colours match the reference.
@@ -26,7 +26,7 @@ constexpr int FWD_BATCH = 64;   // instances staged per pipeline stage
 
 template <int NQ>
 struct FwdSmem {
-    float4 geo[2][FWD_BATCH][2];        // x, y, cx, cy | cz, opacity, cull_hx, cull_hy
+    float4 geo[2][FWD_BATCH][2];        // x, y, cx, cy | cz, opacity, accept_threshold, -
     float4 feat[2][FWD_BATCH][NQ];      // feature rows, zero padded to 4*NQ channels
     uint32_t ids[2][FWD_BATCH];
     float maskv[2][FWD_BATCH];          // DEPTH variant: per-instance mask value
@@ -90,11 +90,6 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     const bool inside = px < (uint32_t)W && py < (uint32_t)H;
     const uint32_t pix_id = (uint32_t)W * py + px;
     const float pixx = (float)px, pixy = (float)py;
-    // pixel-centre bounds of this warp's 8x4 block (warp-uniform): a splat whose accept box (cull_extent)
-    // misses the block is skipped by every lane of the warp with four compares
-    const float bx0 = (float)(blockIdx.x * TILE_X + (warp & 1) * 8), bx1 = bx0 + 7.f;
-    const float by0 = (float)(blockIdx.y * TILE_Y + (warp >> 1) * 4), by1 = by0 + 3.f;
-
     const uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];
     const int total = (int)(range.y - range.x);
     const int nbatch = (total + FWD_BATCH - 1) / FWD_BATCH;
@@ -145,41 +140,41 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         // (C) blend batch b
         if (!__all_sync(0xffffffffu, done)) {
             for (int j = 0; j < cnt; j++) {
+                if ((j & 7) == 0 && j > 0 && __all_sync(0xffffffffu, done)) break;
                 const float4 g0 = sm.geo[stage][j][0];
                 const float4 g1 = sm.geo[stage][j][1];
-                // warp-uniform reject: (g1.z, g1.w) = half extents of the splat's accept box
-                const bool hit = (g0.x + g1.z >= bx0) && (g0.x - g1.z <= bx1) && (g0.y + g1.w >= by0) && (g0.y - g1.w <= by1);
-                if (hit && !done) {
-                    const float dx = g0.x - pixx, dy = g0.y - pixy;
-                    const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
-                    if (!(power > 0.0f)) {
-                        const float alpha = fminf(0.99f, g1.y * expf(power));
-                        if (!(alpha < 1.0f / 255.0f)) {
-                            const float test_T = T * (1 - alpha);
-                            if (test_T < 0.0001f) {
-                                done = true;
-                            } else {
-                                if (COLOR) {
+                const float dx = g0.x - pixx, dy = g0.y - pixy;
+                const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
+                // g1.z = accept_threshold(opacity): below it alpha < 1/255 for certain.  If no live pixel of the warp
+                // can pass the reference's tests, the whole warp skips the splat (and its expf) in one vote.
+                const bool cand = !done && !(power > 0.0f) && (power >= g1.z);
+                if (!__any_sync(0xffffffffu, cand)) continue;
+                if (cand) {
+                    const float alpha = fminf(0.99f, g1.y * expf(power));
+                    if (!(alpha < 1.0f / 255.0f)) {
+                        const float test_T = T * (1 - alpha);
+                        if (test_T < 0.0001f) {
+                            done = true;
+                        } else {
+                            if (COLOR) {
 #pragma unroll
-                                    for (int q = 0; q < NQ; q++) {
-                                        const float4 f = sm.feat[stage][j][q];
-                                        C[4 * q + 0] += f.x * alpha * T;
-                                        C[4 * q + 1] += f.y * alpha * T;
-                                        C[4 * q + 2] += f.z * alpha * T;
-                                        C[4 * q + 3] += f.w * alpha * T;
-                                    }
+                                for (int q = 0; q < NQ; q++) {
+                                    const float4 f = sm.feat[stage][j][q];
+                                    C[4 * q + 0] += f.x * alpha * T;
+                                    C[4 * q + 1] += f.y * alpha * T;
+                                    C[4 * q + 2] += f.z * alpha * T;
+                                    C[4 * q + 3] += f.w * alpha * T;
                                 }
-                                if (MD) {
-                                    Macc += sm.maskv[stage][j] * alpha * T;
-                                    Dacc += sm.depthv[stage][j] * alpha * T;
-                                }
-                                T = test_T;
-                                last_contributor = (uint32_t)(b * FWD_BATCH + j + 1);
                             }
+                            if (MD) {
+                                Macc += sm.maskv[stage][j] * alpha * T;
+                                Dacc += sm.depthv[stage][j] * alpha * T;
+                            }
+                            T = test_T;
+                            last_contributor = (uint32_t)(b * FWD_BATCH + j + 1);
                         }
                     }
                 }
-                if ((j & 7) == 7 && __all_sync(0xffffffffu, done)) break;
             }
         }
 

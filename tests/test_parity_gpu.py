@@ -97,7 +97,7 @@ def _render(sc, K, colors=None, bg=None, opac=None, cov_precomp=None, use_cub=Fa
         bg_t = torch.zeros(max(K, 3)) if bg is None else bg
         rs = R.GaussianRasterizationSettings(sc.H, sc.W, c.tanfovx, c.tanfovy, bg_t.to(dev), 1.0, c.world_view_transform.to(dev),
                                              c.full_proj_transform.to(dev), 0, c.camera_center.to(dev), False, debug)
-        col = (g.colors if colors is None else colors).to(dev).requires_grad_(backward)
+        col = (g.colors if colors is None else colors).to(dev).requires_grad_(True)   # keeps a grad_fn (scratch access)
         kw = dict(scales=g.scales.to(dev), rotations=g.rotations.to(dev)) if cov_precomp is None else dict(cov3D_precomp=cov_precomp.to(dev))
         color, radii = Rast(rs)(means3D=g.means3D.to(dev), means2D=torch.zeros(sc.P, 3, device=dev),
                                 opacities=(g.opacities if opac is None else opac).to(dev), colors_precomp=col, **kw)
