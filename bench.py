@@ -59,53 +59,63 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region, read through NVML from a background thread every
+    `period` seconds (the quantities `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` prints;
+    B200_PROFILING.md recipe).  An in-process NVML handle is used instead of an `nvidia-smi -lms` child because the
+    latter's polling was measured to slow this launch-heavy step by 2-3x, which would falsify the number it guards."""
 
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, index: int):
-        self.index = index
-        self.rows = []
-        self.proc = None
+    def __init__(self, index: int, period: float = 0.1):
+        self.index, self.period = index, period
+        self.rows, self.ok, self._stop = [], False, threading.Event()
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES when mapping the CUDA ordinal to an NVML index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].strip().isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:   # pragma: no cover
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+        if not self.ok:
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, int(rs)))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
 
     def mark(self):
-        """index of the next sample (call at the start / end of the timed region)"""
         return len(self.rows)
 
     def stop(self, i0=0, i1=None):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
-        rows = self.rows[i0:(i1 + 1) if i1 is not None else None] or self.rows[-3:]
-        sm, mx, reasons = [], [], set()
-        for r in rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "?")]}
+        self._stop.set()
+        self.t.join(timeout=1.0)
+        rows = self.rows[i0:(i1 + 1) if i1 is not None else None] or self.rows[-2:]
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        reasons = sorted(n for n, bit in names.items() if any(r[1] & bit for r in rows))
+        sm = [r[0] for r in rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.max_sm), "reasons": reasons,
+                "samples": len(sm), "source": "nvml"}
 
 
 def load_peaks():
@@ -237,8 +247,8 @@ def main():
         return float(ms.item())
 
     # ---------------- warm-up, then the timed regions ----------------
-    # the clock sampler starts BEFORE the warm-up (nvidia-smi start-up perturbs the GPU for ~100 ms) and keeps
-    # sampling every 100 ms; only the samples taken during the timed region are reported
+    # the clock sampler starts BEFORE the warm-up and keeps sampling every 100 ms; only the samples taken
+    # during the timed region are reported
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()

@@ -102,7 +102,9 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     const uint32_t px = tile_x0 + xl, py = tile_y0 + yl;
     const bool inside = px < (uint32_t)W && py < (uint32_t)H;
     const uint32_t pix_id = (uint32_t)W * py + px;
-    const float pixx = (float)px, pixy = (float)py;
+    float pixx = (float)px, pixy = (float)py;
+    // opaque to the optimiser: otherwise nvcc rematerialises both from %ctaid / %tid inside the hot loop
+    asm volatile("" : "+f"(pixx), "+f"(pixy));
     const size_t plane = (size_t)H * W;
 
     const uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];

@@ -89,7 +89,9 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     const uint32_t py = blockIdx.y * TILE_Y + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < (uint32_t)W && py < (uint32_t)H;
     const uint32_t pix_id = (uint32_t)W * py + px;
-    const float pixx = (float)px, pixy = (float)py;
+    float pixx = (float)px, pixy = (float)py;
+    // opaque to the optimiser: otherwise nvcc rematerialises both from %ctaid / %tid inside the hot loop
+    asm volatile("" : "+f"(pixx), "+f"(pixy));
     const uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];
     const int total = (int)(range.y - range.x);
     const int nbatch = (total + FWD_BATCH - 1) / FWD_BATCH;
@@ -139,10 +141,10 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 
         // (C) blend batch b
         if (!__all_sync(0xffffffffu, done)) {
-            for (int j = 0; j < cnt; j++) {
-                if ((j & 7) == 0 && j > 0 && __all_sync(0xffffffffu, done)) break;
-                const float4 g0 = sm.geo[stage][j][0];
-                const float4 g1 = sm.geo[stage][j][1];
+            const float4* gp = &sm.geo[stage][0][0];
+            for (int j = 0; j < cnt; j++, gp += 2) {
+                const float4 g0 = gp[0];
+                const float4 g1 = gp[1];
                 const float dx = g0.x - pixx, dy = g0.y - pixy;
                 const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
                 // g1.z = accept_threshold(opacity): below it alpha < 1/255 for certain.  If no live pixel of the warp
@@ -175,6 +177,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                         }
                     }
                 }
+                if (__all_sync(0xffffffffu, done)) break;   // only reached when some pixel was a candidate
             }
         }
 

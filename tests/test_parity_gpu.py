@@ -106,7 +106,9 @@ def _render(sc, K, colors=None, bg=None, opac=None, cov_precomp=None, use_cub=Fa
             torch.cuda.synchronize()
             return color.detach().cpu(), radii.cpu(), col.grad.cpu()
         torch.cuda.synchronize()
-        return color.detach().cpu(), radii.cpu(), color.grad_fn
+        fn = color.grad_fn   # read the scratch while the outputs are alive (saved outputs are weak references)
+        scratch = (int(fn.num_rendered),) + tuple(fn.saved_tensors[-3:])
+        return color.detach().cpu(), radii.cpu(), scratch
     finally:
         R.set_cub_sort(False)
 
@@ -116,10 +118,8 @@ def test_full_size_properties():
     P, H, W, K = 1_000_000, 1080, 1920, 32
     sc = synthetic.scene(P, H, W, K)
     ones = torch.ones(P, K)
-    col, radii, fn = _render(sc, K, colors=ones)
+    col, radii, (R_, geom, binning, img) = _render(sc, K, colors=ones)
     from seganygaussians_b200 import _lib
-    geom, binning, img = fn.saved_tensors[-3:]
-    R_ = int(fn.num_rendered)
     il, bl, gl = _lib.image_layout(W, H), _lib.binning_layout(R_), _lib.geom_layout(P)
     final_T = img[il.final_T: il.final_T + 4 * H * W].view(torch.float32).view(H, W).cpu()
     # X5 partition of unity: features == 1, bg == 0  ->  out == 1 - final_T on every channel
