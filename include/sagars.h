@@ -66,6 +66,7 @@ enum {
 #define SAGARS_FLAG_MASK_DEPTH 4u    /* DEPTH variant: extra per-Gaussian mask + view-depth channels  */
 #define SAGARS_FLAG_MASK_ONLY 8u     /* DEPTH mask-only path (forward_mask / mask_forward)            */
 #define SAGARS_FLAG_CUB_SORT 16u     /* use cub::DeviceRadixSort instead of the library's own sort    */
+#define SAGARS_FLAG_NO_TENSOR_CORES 32u /* force the fp32 SIMT blend kernels (bit-exact colours) instead of tcgen05 */
 
 /* Allocator callback: return a device pointer to at least `bytes` bytes (256-B aligned), or NULL.
  * Replaces: std::function<char*(size_t)> geometryBuffer / binningBuffer / imageBuffer

@@ -195,6 +195,8 @@ int sort_num_passes(int end_bit);
 int launch_tile_ranges(int R, int num_tiles, const uint64_t* keys, uint2* ranges, cudaStream_t s, bool debug);
 int launch_render_forward(const sagars_forward_args& a, const Dims& d, GeomView g, ImageView im,
                           const uint32_t* point_list, cudaStream_t s, bool debug);
+int launch_render_forward_tc(const sagars_forward_args& a, const Dims& d, GeomView g, ImageView im,
+                             const uint32_t* point_list, cudaStream_t s, bool debug);
 int launch_render_backward(const sagars_backward_args& a, const Dims& d, GeomView g, ImageView im,
                            const uint32_t* point_list, float* ggrad, cudaStream_t s, bool debug);
 int launch_geom_backward(const sagars_backward_args& a, const Dims& d, GeomView g, const float* ggrad,

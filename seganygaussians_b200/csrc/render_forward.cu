@@ -225,6 +225,9 @@ int launch_render_forward(const sagars_forward_args& a, const Dims& d, GeomView 
     const float* features = a.colors_precomp != nullptr ? a.colors_precomp : g.rgb;
     const int K = d.C;
     if (mask_only) return launch_fwd_t<1, false, true, false>(a, d, g, im, point_list, features, s, debug);
+    // K = 32 feature rendering: the channel contraction runs on tcgen05 (render_forward_tc.cu)
+    if (K == 32 && !md && a.colors_precomp != nullptr && !(a.flags & SAGARS_FLAG_NO_TENSOR_CORES))
+        return launch_render_forward_tc(a, d, g, im, point_list, s, debug);
     const bool vec = (K % 4) == 0;
     const int nq = (K + 3) / 4;
 #define SAGARS_FWD_CASE(NQ_)                                                                               \

@@ -98,10 +98,19 @@ def _flags(settings: GaussianRasterizationSettings, extra: int = 0) -> int:
         f |= _lib.FLAG_DEBUG
     if _USE_CUB_SORT:
         f |= _lib.FLAG_CUB_SORT
+    if not _USE_TENSOR_CORES:
+        f |= _lib.FLAG_NO_TENSOR_CORES
     return f
 
 
 _USE_CUB_SORT = False
+_USE_TENSOR_CORES = True
+
+
+def set_tensor_cores(enabled: bool) -> None:
+    """Route the K=32 blend through tcgen05 (default) or through the fp32 SIMT kernels (bit-exact colours)."""
+    global _USE_TENSOR_CORES
+    _USE_TENSOR_CORES = bool(enabled)
 
 
 def set_cub_sort(enabled: bool) -> None:

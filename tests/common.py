@@ -90,12 +90,14 @@ def _leafs(sc, dev, use_sh, use_cov_precomp=False):
 
 
 def run_torch_impl(kind: str, sc, K: int, depth: bool = False, use_sh: bool = False, sh_degree: int = 0,
-                   backward: bool = True, bg=None, debug=False):
-    """kind = 'ours' (libsagars through seganygaussians_b200.rasterizer) or 'ref' (oracle/_ref)."""
+                   backward: bool = True, bg=None, debug=False, tensor_cores: bool = True):
+    """kind = 'ours' (libsagars through seganygaussians_b200.rasterizer) or 'ref' (oracle/_ref).
+    tensor_cores=False routes the K=32 blend through the fp32 SIMT kernels (bit-exact colours)."""
     dev = torch.device("cuda", 0)
     variant = variant_of(K, depth)
     if kind == "ours":
         from seganygaussians_b200 import rasterizer as R
+        R.set_tensor_cores(tensor_cores)
         Settings = R.GaussianRasterizationSettings
         Rast = {"base": R.GaussianRasterizer, "cf": R.GaussianRasterizerContrastiveF, "depth": R.GaussianRasterizerDepth}[variant]
     else:

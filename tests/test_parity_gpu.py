@@ -78,20 +78,25 @@ def test_cuda_matches_live_reference(cfg):
     if not common.have_ref(common.variant_of(K, depth)):
         pytest.skip("oracle/_ref not built (python oracle/build_ref.py where /root/reference is mounted)")
     sc = synthetic.scene(P, H, W, K)
-    ours = common.run_torch_impl("ours", sc, K, depth=depth)
     ref = common.run_torch_impl("ref", sc, K, depth=depth)
-    ok, lines = common.compare(ours, ref, floats=common.FLOAT_FWD + common.GRADS + ("means2D", "conic_opacity", "depths", "cov3D"),
-                               verbose=False)
-    assert ok, "\n".join(lines)
-    # forward images are not merely close: the per-pixel arithmetic is kept operation for operation
-    assert np.array_equal(ours.color, ref.color) and np.array_equal(ours.final_T, ref.final_T)
+    for tensor_cores in (True, False):
+        ours = common.run_torch_impl("ours", sc, K, depth=depth, tensor_cores=tensor_cores)
+        ok, lines = common.compare(ours, ref, floats=common.FLOAT_FWD + common.GRADS + ("means2D", "conic_opacity", "depths", "cov3D"),
+                                   verbose=False)
+        assert ok, f"tensor_cores={tensor_cores}\n" + "\n".join(lines)
+        assert np.array_equal(ours.final_T, ref.final_T)
+        if not tensor_cores:
+            # fp32 SIMT path: images are not merely close, the per-pixel arithmetic is kept operation for operation
+            assert np.array_equal(ours.color, ref.color)
 
 
-def _render(sc, K, colors=None, bg=None, opac=None, cov_precomp=None, use_cub=False, debug=False, backward=False, dL=None):
+def _render(sc, K, colors=None, bg=None, opac=None, cov_precomp=None, use_cub=False, debug=False, backward=False, dL=None,
+            tensor_cores=True):
     from seganygaussians_b200 import rasterizer as R
     dev = torch.device("cuda", 0)
     g, c = sc.gauss, sc.cam
     R.set_cub_sort(use_cub)
+    R.set_tensor_cores(tensor_cores)
     try:
         Rast = R.GaussianRasterizer if K == 3 else R.GaussianRasterizerContrastiveF
         bg_t = torch.zeros(max(K, 3)) if bg is None else bg
@@ -111,6 +116,7 @@ def _render(sc, K, colors=None, bg=None, opac=None, cov_precomp=None, use_cub=Fa
         return color.detach().cpu(), radii.cpu(), scratch
     finally:
         R.set_cub_sort(False)
+        R.set_tensor_cores(True)
 
 
 def test_full_size_properties():
@@ -146,9 +152,12 @@ def test_full_size_properties():
 def test_channel_independence_k32_vs_k3():
     """X1: the first three channels of a K=32 render equal the K=3 render of those channels, bit for bit."""
     sc = synthetic.scene(50000, 270, 480, 32)
-    c32, r32, _ = _render(sc, 32)
+    c32, r32, _ = _render(sc, 32, tensor_cores=False)
     c3, r3, _ = _render(sc, 3, colors=sc.gauss.colors[:, :3].contiguous())
     assert torch.equal(c32[:3], c3) and torch.equal(r32, r3)
+    # and the tensor-core path agrees with it to fp32 rounding (3xTF32)
+    c32_tc, _, _ = _render(sc, 32, tensor_cores=True)
+    assert float((c32_tc - c32).abs().max()) <= 1e-5 * float(c32.abs().max())
 
 
 def test_backward_linearity_full_gradient():

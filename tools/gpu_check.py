@@ -29,6 +29,11 @@ def parity(name, P, H, W, K, depth=False, use_sh=False, deg=0, M=0, with_oracle=
         ours = common.run_torch_impl("ours", sc, K, depth=depth, use_sh=use_sh, sh_degree=deg)
         vis = int((ours.radii > 0).sum())
         print(f"ours: vis={vis} R={ours.num_rendered} n_contrib mean={ours.n_contrib.mean():.1f}")
+        if K == 32 and not depth:
+            simt = common.run_torch_impl("ours", sc, K, depth=depth, use_sh=use_sh, sh_degree=deg, tensor_cores=False)
+            simt.kind = "ours-simt"
+            print("-- tensor-core path vs fp32 SIMT path:")
+            common.compare(ours, simt)
     except Exception:
         traceback.print_exc()
         return False

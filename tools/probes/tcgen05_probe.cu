@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ A,
 
 // ---- variant 2: kind::tf32, 3-term split (hi/lo), A K-major [128 x 16], B MN-major (feature rows [k][n]) ----
 constexpr int K2 = 16;   // instances per batch -> 2 MMAs of K=8 per term
+template <int BMN>
 __global__ void __launch_bounds__(128) probe_tf32_kernel(const float* __restrict__ A, const float* __restrict__ F, float* __restrict__ D,
                                                          int* __restrict__ status)
 {
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(128) probe_tf32_kernel(const float* __restrict
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
     const int tid = threadIdx.x, warp = tid >> 5;
     constexpr uint32_t A_SBO = 128, A_LBO = 128 * (M / 8);
-    constexpr uint32_t B_SBO = 128, B_LBO = 128 * (N / 4);
+    constexpr uint32_t B_SBO = 128, B_LBO = BMN ? 128 * (N / 4) : 128 * (N / 8);
 
     for (int k = 0; k < K2; k++) {
         const float x = A[tid * K2 + k];
@@ -141,7 +142,8 @@ __global__ void __launch_bounds__(128) probe_tf32_kernel(const float* __restrict
         const int k = e / N, n = e % N;
         const float x = F[e];
         const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-        const int off = (k / 8) * (B_LBO / 4) + (n / 4) * (B_SBO / 4) + (k % 8) * 4 + (n % 4);
+        const int off = BMN ? (k / 8) * (B_LBO / 4) + (n / 4) * (B_SBO / 4) + (k % 8) * 4 + (n % 4)
+                            : (k / 4) * (B_LBO / 4) + (n / 8) * (B_SBO / 4) + (n % 8) * 4 + (k % 4);
         sBh[off] = h;
         sBl[off] = x - h;
     }
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(128) probe_tf32_kernel(const float* __restrict
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     // D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), A K-major (bit15=0), B MN-major (bit16=1), N, M
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)BMN << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
     if (tid == 0) {
         int first = 1;
         for (int term = 0; term < 3; term++) {            // lo*hi, hi*lo, hi*hi
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(128) probe_tf32_kernel(const float* __restrict
             const float* b = (term == 1) ? sBl : sBh;
             for (int ks = 0; ks < K2 / 8; ks++) {
                 const uint64_t da = make_desc(smem_u32(a) + ks * 2 * A_LBO, A_LBO, A_SBO);
-                const uint64_t db = make_desc(smem_u32(b) + ks * B_LBO, B_LBO, B_SBO);
+                const uint64_t db = make_desc(smem_u32(b) + (BMN ? ks * B_LBO : ks * 2 * B_LBO), B_LBO, B_SBO);
                 const uint32_t accum = first ? 0u : 1u;
                 first = 0;
                 asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p; }"
@@ -231,16 +233,19 @@ int main()
         cudaMemcpy(dA2, hA2, M * K2 * 4, cudaMemcpyHostToDevice); cudaMemcpy(dF, hF, K2 * N * 4, cudaMemcpyHostToDevice);
         cudaMemset(dD, 0, M * N * 4); st = -1; cudaMemcpy(dS, &st, 4, cudaMemcpyHostToDevice);
         const int smem2 = (2 * M * K2 + 2 * N * K2) * 4 + 64;
-        cudaFuncSetAttribute(probe_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-        probe_tf32_kernel<<<1, 128, smem2>>>(dA2, dF, dD, dS);
+        for (int bmn = 0; bmn < 2; bmn++) {
+        cudaMemset(dD, 0, M * N * 4); st = -1; cudaMemcpy(dS, &st, 4, cudaMemcpyHostToDevice);
+        if (bmn) { cudaFuncSetAttribute(probe_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2); probe_tf32_kernel<1><<<1, 128, smem2>>>(dA2, dF, dD, dS); }
+        else { cudaFuncSetAttribute(probe_tf32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2); probe_tf32_kernel<0><<<1, 128, smem2>>>(dA2, dF, dD, dS); }
         cudaError_t e = cudaDeviceSynchronize();
         cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost); cudaMemcpy(hD, dD, M * N * 4, cudaMemcpyDeviceToHost);
         double err = 0, mx = 0;
         for (int i = 0; i < M * N; i++) { double d = fabs(hD[i] - ref2[i]); if (d > err) err = d; if (fabs(ref2[i]) > mx) mx = fabs(ref2[i]); }
-        printf("tf32x3 (A K-major, B MN-major): cuda=%s status=%d max|ref|=%.3f max err=%.3e  %s\n", cudaGetErrorString(e), st, mx, err,
+        printf("tf32x3 (A K-major, B %s): cuda=%s status=%d max|ref|=%.3f max err=%.3e  %s\n", bmn ? "MN-major" : "K-major", cudaGetErrorString(e), st, mx, err,
                (e == cudaSuccess && st == 0 && err < 2e-5) ? "TF32X3 OK" : "TF32X3 WRONG");
         if (err >= 2e-5) { printf(" D[0][0..3]= %f %f %f %f  ref %f %f %f %f\n", hD[0], hD[1], hD[2], hD[3], ref2[0], ref2[1], ref2[2], ref2[3]);
                            printf(" D[5][0..3]= %f %f %f %f  ref %f %f %f %f\n", hD[160], hD[161], hD[162], hD[163], ref2[160], ref2[161], ref2[162], ref2[163]); }
+        }
     }
     return 0;
 }
