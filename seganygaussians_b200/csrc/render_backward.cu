@@ -12,7 +12,7 @@
 //     pair in which no pixel can pass the reference's tests (conservative lower bound on `power`, see
 //     accept_threshold) is skipped with one warp vote before expf.  Each blended pair appends (w = alpha*T, q = G*dL/dalpha, pixel) to a
 //     compact per-splat list in shared memory (warp ballot + one shared atomic per (warp, splat)).
-//   phase B (a warp per splat, lane = (list slot, channel quad)): every per-Gaussian gradient is a sparse
+//   phase B (warps take splats from a shared counter; lane = (list slot, channel quad)): every per-Gaussian gradient is a sparse
 //     product over the tile's pixels,
 //         dL/dcolour[j][:] = sum_p w[j][p] * g[p][:]          (g tile resident in smem, float4 reads)
 //         moments[j][:]    = sum_p q[j][p] * (1, x, y, x^2, xy, y^2)(p)   (tile-centred pixel coordinates)
@@ -41,6 +41,7 @@ struct BwdSmem {
     float2 ent[BWD_NB][TILE_PIX];       // compact list of blended pairs per instance: (w, q)
     uint8_t entp[BWD_NB][TILE_PIX];     //   ... and their raster-local pixel index
     uint32_t cnt[2][BWD_NB];            // list lengths (double buffered across batches)
+    uint32_t next_inst[2];              // phase-B work counter: warps take instances first come, first served
     float4 geo[2][BWD_NB][2];           // x, y, cx, cy | cz, opacity, accept_threshold, -
     float4 feat[BWD_NB][NQ];            // feature rows, zero padded
     float tabx[16][8];                  // moment basis factors in x: 1, x, 1, x^2, x, 1, 0, 0   (x = xl - 7.5)
@@ -56,6 +57,17 @@ __device__ __forceinline__ void bwd_issue_geo(BwdSmem<NQ>& sm, int stage, int id
     if (tid < cnt * 2) {
         const int j = tid >> 1, h = tid & 1;
         cp_async16(&sm.geo[stage][j][h], geo + 8 * (size_t)sm.ids[idbuf][j] + 4 * h);
+    }
+}
+
+// records past the end of the batch: never accepted (threshold = +inf)
+template <int NQ>
+__device__ __forceinline__ void bwd_pad_geo(BwdSmem<NQ>& sm, int stage, int cnt)
+{
+    const int tid = threadIdx.x;
+    if (tid >= cnt && tid < BWD_NB) {
+        sm.geo[stage][tid][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        sm.geo[stage][tid][1] = make_float4(0.f, 0.f, __int_as_float(0x7f800000), 0.f);
     }
 }
 
@@ -116,6 +128,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     // the tile only needs instances [0, max over its pixels of n_contrib); a warp only [0, its own max)
     if (tid == 0) sm.max_contrib = 0;
     if (tid < 2 * BWD_NB) sm.cnt[tid / BWD_NB][tid % BWD_NB] = 0;
+    if (tid < 2) sm.next_inst[tid] = 0;
     if (tid < 128) {   // moment basis tables
         const int c = tid >> 3, k = tid & 7;
         const float v = (float)c - 7.5f;
@@ -175,6 +188,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     cp_async_commit();
     if (nbatch > 1 && tid < batch_cnt(1)) sm.ids[1][tid] = load_id(1, tid);
     cp_async_wait_all();
+    bwd_pad_geo<NQ>(sm, 0, batch_cnt(0));
     __syncthreads();
 
     float T = T_final;
@@ -202,58 +216,71 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
         const bool have_next_id = (b + 2 < nbatch) && tid < batch_cnt(b + 2);
         if (have_next_id) next_id = load_id(b + 2, tid);
         if (tid < BWD_NB) sm.cnt[stage ^ 1][tid] = 0;
+        if (tid == BWD_NB) sm.next_inst[stage ^ 1] = 0;
 
         // ---------------- phase A: thread = pixel ----------------
         if (pos_hi - (cnt - 1) < warp_n) {   // some pixel of this warp still has contributors in this batch
-            for (int jj = 0; jj < cnt; jj++) {
-                if (pos_hi - jj >= warp_n) continue;                                    // warp-uniform
-                const float4 g0 = sm.geo[stage][jj][0];
-                const float4 g1 = sm.geo[stage][jj][1];
-                const float dx = g0.x - pixx, dy = g0.y - pixy;
-                const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
-                // g1.z = accept_threshold(opacity); one vote rejects the splat for the whole warp before expf
-                const bool cand = (pos_hi - jj < my_n) && !(power > 0.0f) && (power >= g1.z);
-                if (!__any_sync(0xffffffffu, cand)) continue;                           // warp-uniform
-                bool blended = false;
-                float w_out = 0.f, q_out = 0.f;
-                if (cand) {
-                    const float G = expf(power);
-                    const float alpha = fminf(0.99f, g1.y * G);
-                    if (!(alpha < 1.0f / 255.0f)) {
-                        T = T / (1.f - alpha);
-                        w_out = alpha * T;
-                        float s = 0.f;
-                        if (COLOR) {
-                            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four chains instead of one 4*NQ-long one
+            // four splats at a time: independent `power` tests (ILP, one vote per four); the accepted ones are then
+            // taken in order.  Records beyond the batch are sentinels (accept_threshold = +inf).
+            for (int j0 = 0; j0 < cnt; j0 += 4) {
+                if (pos_hi - (j0 + 3) >= warp_n) continue;                              // warp-uniform
+                float pw[4], op[4];
+                bool cd[4];
 #pragma unroll
-                            for (int q = 0; q < NQ; q++) {
-                                const float4 f = sm.feat[jj][q];
-                                s0 += f.x * g[4 * q + 0];
-                                s1 += f.y * g[4 * q + 1];
-                                s2 += f.z * g[4 * q + 2];
-                                s3 += f.w * g[4 * q + 3];
-                            }
-                            s = (s0 + s1) + (s2 + s3);
-                        }
-                        acc = last_alpha * last_s + (1.f - last_alpha) * acc;
-                        last_s = s;
-                        float dL_dalpha = (s - acc) * T;
-                        last_alpha = alpha;
-                        dL_dalpha += (-T_final / (1.f - alpha)) * bgdot;
-                        q_out = G * dL_dalpha;
-                        blended = true;
-                    }
+                for (int i = 0; i < 4; i++) {
+                    const float4 g0 = sm.geo[stage][j0 + i][0];
+                    const float4 g1 = sm.geo[stage][j0 + i][1];
+                    const float dx = g0.x - pixx, dy = g0.y - pixy;
+                    pw[i] = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
+                    cd[i] = (pos_hi - (j0 + i) < my_n) && !(pw[i] > 0.0f) && (pw[i] >= g1.z);
+                    op[i] = g1.y;
                 }
-                const uint32_t m = __ballot_sync(0xffffffffu, blended);
-                if (m != 0u) {
-                    const int leader = __ffs(m) - 1;
-                    uint32_t base = 0;
-                    if (lane == leader) base = atomicAdd(&sm.cnt[stage][jj], (uint32_t)__popc(m));
-                    base = __shfl_sync(0xffffffffu, base, leader);
-                    if (blended) {
-                        const uint32_t e = base + __popc(m & lt_mask);
-                        sm.ent[jj][e] = make_float2(w_out, q_out);
-                        sm.entp[jj][e] = (uint8_t)rl;
+                if (!__any_sync(0xffffffffu, cd[0] || cd[1] || cd[2] || cd[3])) continue;   // warp-uniform
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (!__any_sync(0xffffffffu, cd[i])) continue;                      // warp-uniform
+                    const int jj = j0 + i;
+                    bool blended = false;
+                    float w_out = 0.f, q_out = 0.f;
+                    if (cd[i]) {
+                        const float G = expf(pw[i]);
+                        const float alpha = fminf(0.99f, op[i] * G);
+                        if (!(alpha < 1.0f / 255.0f)) {
+                            T = T / (1.f - alpha);
+                            w_out = alpha * T;
+                            float s = 0.f;
+                            if (COLOR) {
+                                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four chains instead of one 4*NQ-long one
+#pragma unroll
+                                for (int q = 0; q < NQ; q++) {
+                                    const float4 f = sm.feat[jj][q];
+                                    s0 += f.x * g[4 * q + 0];
+                                    s1 += f.y * g[4 * q + 1];
+                                    s2 += f.z * g[4 * q + 2];
+                                    s3 += f.w * g[4 * q + 3];
+                                }
+                                s = (s0 + s1) + (s2 + s3);
+                            }
+                            acc = last_alpha * last_s + (1.f - last_alpha) * acc;
+                            last_s = s;
+                            float dL_dalpha = (s - acc) * T;
+                            last_alpha = alpha;
+                            dL_dalpha += (-T_final / (1.f - alpha)) * bgdot;
+                            q_out = G * dL_dalpha;
+                            blended = true;
+                        }
+                    }
+                    const uint32_t m = __ballot_sync(0xffffffffu, blended);
+                    if (m != 0u) {
+                        const int leader = __ffs(m) - 1;
+                        uint32_t base = 0;
+                        if (lane == leader) base = atomicAdd(&sm.cnt[stage][jj], (uint32_t)__popc(m));
+                        base = __shfl_sync(0xffffffffu, base, leader);
+                        if (blended) {
+                            const uint32_t e = base + __popc(m & lt_mask);
+                            sm.ent[jj][e] = make_float2(w_out, q_out);
+                            sm.entp[jj][e] = (uint8_t)rl;
+                        }
                     }
                 }
             }
@@ -267,7 +294,11 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
         }
 
         // ---------------- phase B: a warp per instance, lane = (list slot, channel quad / moment) ----------------
-        for (int jj = warp; jj < cnt; jj += 8) {
+        for (;;) {
+            int jj = 0;
+            if (lane == 0) jj = (int)atomicAdd(&sm.next_inst[stage], 1u);
+            jj = __shfl_sync(0xffffffffu, jj, 0);
+            if (jj >= cnt) break;                                                       // warp-uniform
             const int n = (int)sm.cnt[stage][jj];
             if (n == 0) continue;                                                       // warp-uniform
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -341,6 +372,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
         // publish ids(b+2); wait for the copies of batch b+1
         if (have_next_id) sm.ids[(b + 2) % 3][tid] = next_id;
         cp_async_wait_all();
+        if (b + 1 < nbatch) bwd_pad_geo<NQ>(sm, stage ^ 1, batch_cnt(b + 1));
         __syncthreads();
     }
 }

@@ -71,6 +71,17 @@ __device__ __forceinline__ void fwd_issue_batch(FwdSmem<NQ>& sm, int stage, int 
     }
 }
 
+// records past the end of the tile's list (up to the next multiple of 4): never accepted (threshold = +inf)
+template <int NQ>
+__device__ __forceinline__ void fwd_pad_batch(FwdSmem<NQ>& sm, int stage, int cnt)
+{
+    const int tid = threadIdx.x;
+    if (tid >= cnt && tid < FWD_BATCH) {
+        sm.geo[stage][tid][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        sm.geo[stage][tid][1] = make_float4(0.f, 0.f, __int_as_float(0x7f800000), 0.f);
+    }
+}
+
 template <int NQ, bool VEC, bool MD, bool COLOR>
 __global__ void __launch_bounds__(TILE_PIX)
 render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
@@ -118,6 +129,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         cp_async_commit();
         if (nbatch > 1 && tid < min(FWD_BATCH, total - FWD_BATCH)) sm.ids[1][tid] = point_list[range.x + FWD_BATCH + tid];
         cp_async_wait_all();
+        fwd_pad_batch<NQ>(sm, 0, min(FWD_BATCH, total));
         __syncthreads();
     }
 
@@ -141,39 +153,50 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 
         // (C) blend batch b
         if (!__all_sync(0xffffffffu, done)) {
+            // four splats at a time: independent `power` tests (ILP, one vote per four), accepted ones taken in order.
+            // Records beyond the tile's list are sentinels (accept_threshold = +inf): no bounds checks needed.
             const float4* gp = &sm.geo[stage][0][0];
-            for (int j = 0; j < cnt; j++, gp += 2) {
-                const float4 g0 = gp[0];
-                const float4 g1 = gp[1];
-                const float dx = g0.x - pixx, dy = g0.y - pixy;
-                const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
-                // g1.z = accept_threshold(opacity): below it alpha < 1/255 for certain.  If no live pixel of the warp
-                // can pass the reference's tests, the whole warp skips the splat (and its expf) in one vote.
-                const bool cand = !done && !(power > 0.0f) && (power >= g1.z);
-                if (!__any_sync(0xffffffffu, cand)) continue;
-                if (cand) {
-                    const float alpha = fminf(0.99f, g1.y * expf(power));
-                    if (!(alpha < 1.0f / 255.0f)) {
-                        const float test_T = T * (1 - alpha);
-                        if (test_T < 0.0001f) {
-                            done = true;
-                        } else {
-                            if (COLOR) {
+            for (int j0 = 0; j0 < cnt; j0 += 4, gp += 8) {
+                float pw[4], op[4];
+                bool cd[4];
 #pragma unroll
-                                for (int q = 0; q < NQ; q++) {
-                                    const float4 f = sm.feat[stage][j][q];
-                                    C[4 * q + 0] += f.x * alpha * T;
-                                    C[4 * q + 1] += f.y * alpha * T;
-                                    C[4 * q + 2] += f.z * alpha * T;
-                                    C[4 * q + 3] += f.w * alpha * T;
+                for (int i = 0; i < 4; i++) {
+                    const float4 g0 = gp[2 * i];
+                    const float4 g1 = gp[2 * i + 1];
+                    const float dx = g0.x - pixx, dy = g0.y - pixy;
+                    pw[i] = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
+                    cd[i] = !(pw[i] > 0.0f) && (pw[i] >= g1.z);
+                    op[i] = g1.y;
+                }
+                const bool anyc = (cd[0] || cd[1] || cd[2] || cd[3]) && !done;
+                if (!__any_sync(0xffffffffu, anyc)) continue;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (cd[i] && !done) {
+                        const int j = j0 + i;
+                        const float alpha = fminf(0.99f, op[i] * expf(pw[i]));
+                        if (!(alpha < 1.0f / 255.0f)) {
+                            const float test_T = T * (1 - alpha);
+                            if (test_T < 0.0001f) {
+                                done = true;
+                            } else {
+                                if (COLOR) {
+#pragma unroll
+                                    for (int q = 0; q < NQ; q++) {
+                                        const float4 f = sm.feat[stage][j][q];
+                                        C[4 * q + 0] += f.x * alpha * T;
+                                        C[4 * q + 1] += f.y * alpha * T;
+                                        C[4 * q + 2] += f.z * alpha * T;
+                                        C[4 * q + 3] += f.w * alpha * T;
+                                    }
                                 }
+                                if (MD) {
+                                    Macc += sm.maskv[stage][j] * alpha * T;
+                                    Dacc += sm.depthv[stage][j] * alpha * T;
+                                }
+                                T = test_T;
+                                last_contributor = (uint32_t)(b * FWD_BATCH + j + 1);
                             }
-                            if (MD) {
-                                Macc += sm.maskv[stage][j] * alpha * T;
-                                Dacc += sm.depthv[stage][j] * alpha * T;
-                            }
-                            T = test_T;
-                            last_contributor = (uint32_t)(b * FWD_BATCH + j + 1);
                         }
                     }
                 }
@@ -184,6 +207,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         // (D) publish ids(b+2); wait for batch b+1
         if (have_next_id) sm.ids[b & 1][tid] = next_id;
         cp_async_wait_all();
+        if (b + 1 < nbatch) fwd_pad_batch<NQ>(sm, stage ^ 1, min(FWD_BATCH, total - (b + 1) * FWD_BATCH));
         __syncthreads();
     }
 

@@ -51,6 +51,16 @@ __device__ __forceinline__ void tcf_issue_batch(FwdTcSmem& sm, int stage, int id
     }
 }
 
+// records past the end of the tile's list: can never be accepted (threshold = +inf), contribute w = 0
+__device__ __forceinline__ void tcf_pad_batch(FwdTcSmem& sm, int stage, int cnt)
+{
+    const int tid = threadIdx.x;
+    if (tid >= cnt && tid < TCF_BATCH) {
+        sm.geo[stage][tid][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        sm.geo[stage][tid][1] = make_float4(0.f, 0.f, __int_as_float(0x7f800000), 0.f);
+    }
+}
+
 __global__ void __launch_bounds__(TILE_PIX, 3)
 render_forward_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
                          const float* __restrict__ geo, const float* __restrict__ features, const float* __restrict__ bg,
@@ -106,6 +116,7 @@ render_forward_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __res
         cp_async_commit();
         if (nbatch > 1 && tid < min(TCF_BATCH, total - TCF_BATCH)) sm.ids[1][tid] = point_list[range.x + TCF_BATCH + tid];
         cp_async_wait_all();
+        tcf_pad_batch(sm, 0, min(TCF_BATCH, total));
         __syncthreads();
     }
 
@@ -127,26 +138,37 @@ render_forward_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __res
             // ---- scalar part: w[j] = alpha * T of this pixel for the 16 splats of the sub-batch (0 if rejected) ----
             float w[TCF_SUB];
             const float4* gp = &sm.geo[stage][sb][0];
+            // four splats at a time: their `power` tests are independent (ILP, one vote per four); only the accepted
+            // ones are then taken in order, because T and `done` chain through them.  Records beyond the tile's list
+            // are sentinels (accept_threshold = +inf), so no bounds checks are needed here.
 #pragma unroll
-            for (int j = 0; j < TCF_SUB; j++) {
-                w[j] = 0.f;
-                if (sb + j < cnt) {                                   // CTA-uniform
-                    const float4 g0 = gp[2 * j];
-                    const float4 g1 = gp[2 * j + 1];
+            for (int j0 = 0; j0 < TCF_SUB; j0 += 4) {
+                float pw[4], op[4];
+                bool cd[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float4 g0 = gp[2 * (j0 + i)];
+                    const float4 g1 = gp[2 * (j0 + i) + 1];
                     const float dx = g0.x - pixx, dy = g0.y - pixy;
-                    const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
-                    const bool cand = !done && !(power > 0.0f) && (power >= g1.z);
-                    if (__any_sync(0xffffffffu, cand)) {
-                        if (cand) {
-                            const float alpha = fminf(0.99f, g1.y * expf(power));
+                    pw[i] = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
+                    cd[i] = !(pw[i] > 0.0f) && (pw[i] >= g1.z);
+                    op[i] = g1.y;
+                    w[j0 + i] = 0.f;
+                }
+                const bool anyc = (cd[0] || cd[1] || cd[2] || cd[3]) && !done;
+                if (__any_sync(0xffffffffu, anyc)) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        if (cd[i] && !done) {
+                            const float alpha = fminf(0.99f, op[i] * expf(pw[i]));
                             if (!(alpha < 1.0f / 255.0f)) {
                                 const float test_T = T * (1 - alpha);
                                 if (test_T < 0.0001f) {
                                     done = true;
                                 } else {
-                                    w[j] = alpha * T;
+                                    w[j0 + i] = alpha * T;
                                     T = test_T;
-                                    last_contributor = (uint32_t)(b * TCF_BATCH + sb + j + 1);
+                                    last_contributor = (uint32_t)(b * TCF_BATCH + sb + j0 + i + 1);
                                 }
                             }
                         }
@@ -208,6 +230,7 @@ render_forward_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __res
 
         if (have_next_id) sm.ids[b & 1][tid] = next_id;
         cp_async_wait_all();
+        if (b + 1 < nbatch) tcf_pad_batch(sm, stage ^ 1, min(TCF_BATCH, total - (b + 1) * TCF_BATCH));
         __syncthreads();
     }
 
