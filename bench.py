@@ -59,20 +59,20 @@ def parse():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons during the timed region, read through NVML from a background thread every
-    `period` seconds (the quantities `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` prints;
-    B200_PROFILING.md recipe).  An in-process NVML handle is used instead of an `nvidia-smi -lms` child because the
-    latter's polling was measured to slow this launch-heavy step by 2-3x, which would falsify the number it guards."""
+    """SM clock and throttle reasons DURING the timed region, read through NVML (the quantities
+    `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` prints; B200_PROFILING.md recipe).
+    Samples are taken explicitly from the launching thread while the GPU is busy with the timed steps (after
+    the launches of the middle step and of the last step, before the closing synchronise).  A polling child /
+    thread is deliberately NOT used: `nvidia-smi -lms 50` was measured to slow this launch-heavy step 3x and a
+    100 ms NVML thread still added up to ~1 ms/step of jitter, which would falsify the number it guards."""
 
-    def __init__(self, index: int, period: float = 0.1):
-        self.index, self.period = index, period
-        self.rows, self.ok, self._stop = [], False, threading.Event()
+    def __init__(self, index: int):
+        self.index, self.rows, self.ok = index, [], False
         try:
             import pynvml
             self.nv = pynvml
             pynvml.nvmlInit()
-            # honour CUDA_VISIBLE_DEVICES when mapping the CUDA ordinal to an NVML index
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")   # CUDA ordinal -> NVML index
             phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].strip().isdigit() else index
             self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
@@ -80,42 +80,30 @@ class ClockSampler:
         except Exception as e:   # pragma: no cover
             self.err = repr(e)
 
-    def start(self):
+    def sample(self):
         if not self.ok:
             return
-        self.t = threading.Thread(target=self._run, daemon=True)
-        self.t.start()
-
-    def _run(self):
         nv = self.nv
-        while not self._stop.is_set():
-            try:
-                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
-                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.rows.append((sm, int(rs)))
-            except Exception:
-                pass
-            self._stop.wait(self.period)
+        try:
+            sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+            rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.rows.append((sm, int(rs)))
+        except Exception:
+            pass
 
-    def mark(self):
-        return len(self.rows)
-
-    def stop(self, i0=0, i1=None):
+    def result(self):
         if not self.ok:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "?")]}
-        self._stop.set()
-        self.t.join(timeout=1.0)
-        rows = self.rows[i0:(i1 + 1) if i1 is not None else None] or self.rows[-2:]
         nv = self.nv
         names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
                  "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
                  "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
                  "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
-        reasons = sorted(n for n, bit in names.items() if any(r[1] & bit for r in rows))
-        sm = [r[0] for r in rows]
+        reasons = sorted(n for n, bit in names.items() if any(r[1] & bit for r in self.rows))
+        sm = [r[0] for r in self.rows]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.max_sm), "reasons": reasons,
-                "samples": len(sm), "source": "nvml"}
+                "samples": len(sm), "source": "nvml, sampled while the timed steps execute"}
 
 
 def load_peaks():
@@ -233,12 +221,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps):
+    def timed(fn, steps, sampler=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
+        for i in range(steps):
             fn()
+            if sampler is not None and (i == steps // 2 or i == steps - 1):
+                sampler.sample()          # the GPU is still executing this step's backward
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -247,11 +237,7 @@ def main():
         return float(ms.item())
 
     # ---------------- warm-up, then the timed regions ----------------
-    # the clock sampler starts BEFORE the warm-up and keeps sampling every 100 ms; only the samples taken
-    # during the timed region are reported
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
     for _ in range(max(a.warmup, 3)):
         step_resident()
     step_e2e()
@@ -260,9 +246,7 @@ def main():
         _lib.reset_launch_count()
         _lib.profile_read(reset=True)
         _lib.profile_enable(True)
-    i0 = sampler.mark() if sampler else 0
-    ms_total = timed(step_resident, a.steps)
-    i1 = sampler.mark() if sampler else 0
+    ms_total = timed(step_resident, a.steps, sampler)
     stage = None
     launches = None
     if a.impl == "ours":
@@ -270,7 +254,7 @@ def main():
         stage = _lib.profile_read(reset=True)
         launches = _lib.launch_count()
     ms_e2e = timed(step_e2e, a.steps)
-    clocks = sampler.stop(i0, i1) if sampler else None
+    clocks = sampler.result() if sampler else None
 
     n_used = world if use_dist else 1
     gp_per_step = float(P) * H * W * n_used
