@@ -342,7 +342,11 @@ int sagars_backward(const sagars_backward_args* a, void* stream_)
     SAGARS_CUDA(cudaMemsetAsync(ggrad, 0, (size_t)d.P * GG_STRIDE * sizeof(float), s));
     if (!mask_only) SAGARS_CUDA(cudaMemsetAsync(a->dL_dcolors, 0, (size_t)d.P * d.C * sizeof(float), s));
     if (a->R > 0) {
-        { ProfScope ps(ST_RENDER_BWD, s); rc = launch_render_backward(*a, d, g, im, point_list, ggrad, s, debug); }
+        {
+            ProfScope ps(ST_RENDER_BWD, s);
+            rc = (a->flags & SAGARS_FLAG_NO_TENSOR_CORES) ? launch_render_backward(*a, d, g, im, point_list, ggrad, s, debug)
+                                                          : launch_render_backward_mma(*a, d, g, im, point_list, ggrad, s, debug);
+        }
         if (rc) return rc;
     }
     if (mask_only) {
