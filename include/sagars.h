@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SAGARS_ABI_VERSION 1
+#define SAGARS_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SAGARS_API __attribute__((visibility("default")))
@@ -103,6 +103,15 @@ typedef struct sagars_forward_args {
     float* out_mask;            /* [1,H,W] DEPTH only                                                */
     float* out_depth;           /* [1,H,W] DEPTH only                                                */
     int32_t* radii;             /* [P]; written in full                                              */
+    /* Speculative binning (0 = off: size the binning buffer from the exact instance count after the
+     * host read-back, exactly like the reference, CF rasterizer_impl.cu:280-285).  When > 0 the binning
+     * buffer is requested for `binning_capacity_hint` instances BEFORE the read-back and sort / ranges /
+     * blend are queued behind it reading the count from device memory, so the GPU keeps working while
+     * the host waits for the count.  If the count turns out larger than the hint, the queued kernels
+     * skip their work, the allocator is called again with the exact size and the stages are re-issued:
+     * results are identical either way; only the size of the binning buffer differs. */
+    int32_t binning_capacity_hint;
+    int32_t* binning_capacity_out; /* host, optional: capacity the binning buffer was finally laid out for */
 } sagars_forward_args;
 
 /* Forward: preprocess -> scan -> duplicate keys -> radix sort -> tile ranges -> per-tile blend.

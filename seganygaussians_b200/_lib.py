@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsagars.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # flags (include/sagars.h)
 FLAG_PREFILTERED = 1
@@ -40,6 +40,7 @@ class ForwardArgs(C.Structure):
         ("mask", _fp), ("scales", _fp), ("rotations", _fp), ("cov3D_precomp", _fp),
         ("viewmatrix", _fp), ("projmatrix", _fp), ("cam_pos", _fp),
         ("out_color", _fp), ("out_mask", _fp), ("out_depth", _fp), ("radii", _fp),
+        ("binning_capacity_hint", C.c_int32), ("binning_capacity_out", C.POINTER(C.c_int32)),
     ]
 
 

@@ -86,6 +86,34 @@ static double now_us()
     return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
 }
 
+// per-thread pinned landing buffer and event for the forward's single host read-back
+static uint32_t* pinned_status()
+{
+    thread_local uint32_t* p = nullptr;
+    if (!p && cudaHostAlloc((void**)&p, 64, cudaHostAllocDefault) != cudaSuccess) p = nullptr;
+    return p;
+}
+static cudaEvent_t sync_event()
+{
+    thread_local cudaEvent_t ev = nullptr;
+    thread_local int ev_dev = -1;
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (ev && ev_dev != dev) { cudaEventDestroy(ev); ev = nullptr; }
+    if (!ev) {
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) ev = nullptr;
+        ev_dev = dev;
+    }
+    return ev;
+}
+// SAGARS_SYNC=block: cudaStreamSynchronize; default: poll the event
+static int sync_mode()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SAGARS_SYNC"); v = (e && e[0] == 'b') ? 1 : 0; }
+    return v;
+}
+
 // same rule as the reference's getHigherMsb (CF rasterizer_impl.cu:35-50): bits needed for tile ids
 static uint32_t higher_msb(uint32_t n)
 {
@@ -134,12 +162,22 @@ const char* sagars_profile_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ?
 int sagars_profile_read(double* ms_out, int64_t* count_out, int reset)
 {
     std::lock_guard<std::mutex> lk(g_prof_mu);
-    for (auto& r : g_prof_recs) {
+    double gap_ms[ST_COUNT] = {0.0};
+    for (size_t i = 0; i < g_prof_recs.size(); i++) {
+        auto& r = g_prof_recs[i];
         float ms = 0.f;
         if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
             g_prof_ms[r.stage] += ms;
             g_prof_n[r.stage] += 1;
         }
+        float gap = 0.f;   // stream time between the previous stage's end and this stage's start (SAGARS_TRACE only)
+        if (trace_on() && i > 0 && cudaEventElapsedTime(&gap, g_prof_recs[i - 1].b, r.a) == cudaSuccess) gap_ms[r.stage] += gap;
+    }
+    if (trace_on() && !g_prof_recs.empty()) {
+        for (int i = 0; i < ST_COUNT; i++)
+            fprintf(stderr, "[sagars] stream gap before %-16s total %9.3f ms over %zu records\n", kStageNames[i], gap_ms[i], g_prof_recs.size());
+    }
+    for (auto& r : g_prof_recs) {
         g_prof_pool.push_back(r.a);
         g_prof_pool.push_back(r.b);
     }
@@ -248,54 +286,87 @@ int sagars_forward(const sagars_forward_args* a,
     { ProfScope ps(ST_SCAN, s); rc = launch_scan_block_sums(d, g, s, debug); }
     if (rc) return rc;
 
-    // the one host synchronisation of the forward pass: R sizes the binning buffer
-    uint32_t status_h[2] = {0, 0};
+    // The one host read-back of the forward pass: R sizes the binning buffer (CF rasterizer_impl.cu:280-285).
+    // The copy lands in pinned memory and the wait polls an event.  With a capacity hint the remaining stages are
+    // queued BEFORE the wait (they read R from device memory), so the GPU keeps working while the host wakes up.
     if (tr) t2 = now_us();
-    SAGARS_CUDA(cudaMemcpyAsync(status_h, g.status, sizeof(status_h), cudaMemcpyDeviceToHost, s));
-    SAGARS_CUDA(cudaStreamSynchronize(s));
-    if (tr) t3 = now_us();
-    if (status_h[0] != 0) {
-        set_error("Point is filtered although prefiltered is set. This shouldn't happen!");
-        return SAGARS_EPREFILTER;
-    }
-    const int R = (int)status_h[1];
-    *num_rendered = R;
-
-    void* bin_mem = binning_alloc(binning_user, binning_total((size_t)R));
-    if (!bin_mem) { set_error("allocator callback returned NULL"); return SAGARS_EALLOC; }
-    BinningView bv = binning_view(bin_mem, (size_t)R);
-    if (tr) t4 = now_us();
+    uint32_t* pin = pinned_status();
+    cudaEvent_t ev = sync_event();
+    if (!pin || !ev) { set_error("cannot allocate the pinned status buffer"); return SAGARS_ECUDA; }
+    SAGARS_CUDA(cudaMemcpyAsync(pin, g.status, 8, cudaMemcpyDeviceToHost, s));
+    SAGARS_CUDA(cudaEventRecord(ev, s));
+    auto wait_count = [&](int* R_out) -> int {
+        if (sync_mode() == 1) {
+            SAGARS_CUDA(cudaStreamSynchronize(s));
+        } else {
+            cudaError_t q;
+            while ((q = cudaEventQuery(ev)) == cudaErrorNotReady) {}
+            SAGARS_CUDA(q);
+        }
+        if (pin[0] != 0) {
+            set_error("Point is filtered although prefiltered is set. This shouldn't happen!");
+            return SAGARS_EPREFILTER;
+        }
+        *R_out = (int)pin[1];
+        return SAGARS_OK;
+    };
 
     const int num_tiles = d.tiles_x * d.tiles_y;
     const int end_bit = 32 + (int)higher_msb((uint32_t)num_tiles);
     const bool use_cub = (a->flags & SAGARS_FLAG_CUB_SORT) != 0;
-    if (R > 0) {
-        // own sort: emit into the buffer from which an npass-long ping-pong ends in the final arrays
-        const bool start_alt = !use_cub && (sort_num_passes(end_bit) & 1);
-        uint64_t* k0 = start_alt ? bv.keys_alt : bv.point_list_keys;
-        uint32_t* v0 = start_alt ? bv.vals_alt : bv.point_list;
-        { ProfScope ps(ST_DUPLICATE, s); rc = launch_duplicate(d, g, a->radii, k0, v0, s, debug); }
+    bool speculative = a->binning_capacity_hint > 0 && !use_cub && !debug;
+    int R = 0, cap = 0;
+    if (speculative) {
+        cap = a->binning_capacity_hint;
+    } else {
+        rc = wait_count(&R);
         if (rc) return rc;
-        bool in_a = true;
-        {
-            ProfScope ps(ST_SORT, s);
-            rc = launch_sort_pairs(R, end_bit, bv.point_list_keys, bv.point_list, bv.keys_alt, bv.vals_alt, bv.sort_temp,
-                                   sort_temp_bytes((size_t)R), use_cub, &in_a, s, debug);
-        }
-        if (rc) return rc;
-        if (!in_a) {
-            SAGARS_CUDA(cudaMemcpyAsync(bv.point_list_keys, bv.keys_alt, (size_t)R * 8, cudaMemcpyDeviceToDevice, s));
-            SAGARS_CUDA(cudaMemcpyAsync(bv.point_list, bv.vals_alt, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
-        }
+        cap = R;
     }
-    { ProfScope ps(ST_RANGES, s); rc = launch_tile_ranges(R, num_tiles, bv.point_list_keys, im.ranges, s, debug); }
-    if (rc) return rc;
-    { ProfScope ps(ST_RENDER_FWD, s); rc = launch_render_forward(*a, d, g, im, bv.point_list, s, debug); }
-    if (rc) return rc;
+    if (tr) t3 = now_us();
+    for (;;) {
+        void* bin_mem = binning_alloc(binning_user, binning_total((size_t)cap));
+        if (!bin_mem) { set_error("allocator callback returned NULL"); return SAGARS_EALLOC; }
+        BinningView bv = binning_view(bin_mem, (size_t)cap);
+        const uint32_t* n_dev = speculative ? g.status + 1 : nullptr;   // exact layout: the host-side count is the count
+        if (cap > 0) {
+            // own sort: emit into the buffer from which an npass-long ping-pong ends in the final arrays
+            const bool start_alt = !use_cub && (sort_num_passes(end_bit) & 1);
+            uint64_t* k0 = start_alt ? bv.keys_alt : bv.point_list_keys;
+            uint32_t* v0 = start_alt ? bv.vals_alt : bv.point_list;
+            { ProfScope ps(ST_DUPLICATE, s); rc = launch_duplicate(d, g, a->radii, k0, v0, n_dev, cap, s, debug); }
+            if (rc) return rc;
+            bool in_a = true;
+            {
+                ProfScope ps(ST_SORT, s);
+                rc = launch_sort_pairs(n_dev, cap, end_bit, bv.point_list_keys, bv.point_list, bv.keys_alt, bv.vals_alt,
+                                       bv.sort_temp, sort_temp_bytes((size_t)cap), use_cub, &in_a, s, debug);
+            }
+            if (rc) return rc;
+            if (!in_a) {
+                SAGARS_CUDA(cudaMemcpyAsync(bv.point_list_keys, bv.keys_alt, (size_t)cap * 8, cudaMemcpyDeviceToDevice, s));
+                SAGARS_CUDA(cudaMemcpyAsync(bv.point_list, bv.vals_alt, (size_t)cap * 4, cudaMemcpyDeviceToDevice, s));
+            }
+        }
+        { ProfScope ps(ST_RANGES, s); rc = launch_tile_ranges(n_dev, cap, num_tiles, bv.point_list_keys, im.ranges, s, debug); }
+        if (rc) return rc;
+        { ProfScope ps(ST_RENDER_FWD, s); rc = launch_render_forward(*a, d, g, im, bv.point_list, s, debug); }
+        if (rc) return rc;
+        if (!speculative) break;
+        rc = wait_count(&R);
+        if (rc) return rc;
+        if (R <= cap) break;
+        // the hint was too small: the queued stages saw the overflow and did nothing; lay the buffer out exactly
+        speculative = false;
+        cap = R;
+    }
+    if (tr) t4 = now_us();
+    *num_rendered = R;
+    if (a->binning_capacity_out) *a->binning_capacity_out = cap;
     if (tr) {
         t5 = now_us();
-        fprintf(stderr, "[sagars trace] fwd host us: alloc(geom,img)=%.0f launch(pre,scan)=%.0f d2h+sync=%.0f alloc(binning)=%.0f "
-                        "launch(rest)=%.0f total=%.0f\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t5 - t0);
+        fprintf(stderr, "[sagars trace] fwd host us: alloc(geom,img)=%.0f launch(pre,scan)=%.0f wait-before=%.0f rest(+wait)=%.0f "
+                        "total=%.0f\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t0);
     }
     return SAGARS_OK;
 }
@@ -392,7 +463,7 @@ int sagars_sort_pairs(int32_t device, int32_t n, int32_t end_bit, const uint64_t
     SAGARS_CUDA(cudaMemcpyAsync(start_alt ? keys_alt : keys_out, keys_in, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
     SAGARS_CUDA(cudaMemcpyAsync(start_alt ? vals_alt : vals_out, vals_in, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
     bool in_a = true;
-    int rc = launch_sort_pairs(n, end_bit, keys_out, vals_out, keys_alt, vals_alt, stemp, sort_temp_bytes((size_t)n),
+    int rc = launch_sort_pairs(nullptr, n, end_bit, keys_out, vals_out, keys_alt, vals_alt, stemp, sort_temp_bytes((size_t)n),
                                use_cub != 0, &in_a, s, false);
     if (rc) return rc;
     if (!in_a) {

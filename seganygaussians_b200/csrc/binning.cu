@@ -16,6 +16,17 @@
 
 namespace sagars {
 
+// Element count of the binning arrays as the kernels see it.  `n_dev == nullptr`: the host knows it (`cap`).
+// Otherwise the count lives in device memory (written by the scan) and `cap` is the capacity the arrays were
+// laid out for; a count above the capacity means the speculative layout was too small: every kernel then
+// does nothing and the host re-issues the stages with the exact size (api.cu).
+__device__ __forceinline__ int live_count(const uint32_t* __restrict__ n_dev, int cap)
+{
+    if (n_dev == nullptr) return cap;
+    const uint32_t n = *n_dev;
+    return n > (uint32_t)cap ? 0 : (int)n;
+}
+
 // ---------------------------------------------------------------------------------------------
 // exclusive scan of the per-preprocess-block sums (<= a few thousand entries): one CTA
 // ---------------------------------------------------------------------------------------------
@@ -79,7 +90,7 @@ duplicate_kernel(int P, const float* __restrict__ geo, const float* __restrict__
                  const uint32_t* __restrict__ tiles_touched,
                  const uint32_t* __restrict__ block_excl, const int32_t* __restrict__ radii,
                  uint32_t* __restrict__ point_offsets, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                 int tiles_x, int tiles_y)
+                 int tiles_x, int tiles_y, const uint32_t* __restrict__ n_dev, int cap)
 {
     __shared__ uint32_t warp_tot[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -100,6 +111,7 @@ duplicate_kernel(int P, const float* __restrict__ geo, const float* __restrict__
     if (idx >= P) return;
     point_offsets[idx] = incl;
     if (n == 0) return;
+    if (n_dev != nullptr && *n_dev > (uint32_t)cap) return;   // layout too small: nothing may be written
 
     uint32_t off = incl - n;
     const float4 r0 = *reinterpret_cast<const float4*>(geo + 8 * (size_t)idx);
@@ -117,11 +129,11 @@ duplicate_kernel(int P, const float* __restrict__ geo, const float* __restrict__
 }
 
 int launch_duplicate(const Dims& d, GeomView g, const int32_t* radii, uint64_t* keys, uint32_t* vals,
-                     cudaStream_t s, bool debug)
+                     const uint32_t* n_dev, int cap, cudaStream_t s, bool debug)
 {
     const int nblk = (d.P + 255) / 256;
     duplicate_kernel<<<nblk, 256, 0, s>>>(d.P, g.geo, g.depths, g.tiles_touched, g.block_sums, radii, g.point_offsets,
-                                          keys, vals, d.tiles_x, d.tiles_y);
+                                          keys, vals, d.tiles_x, d.tiles_y, n_dev, cap);
     SAGARS_LAUNCH_CHECK(s, debug);
     return SAGARS_OK;
 }
@@ -130,10 +142,12 @@ int launch_duplicate(const Dims& d, GeomView g, const int32_t* radii, uint64_t* 
 // stable LSD radix sort of (u64 key, u32 value), 8-bit digits
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-radix_hist_kernel(const uint64_t* __restrict__ keys, int n, int shift, uint32_t* __restrict__ counts, int nblk)
+radix_hist_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ n_dev, int cap, int shift,
+                  uint32_t* __restrict__ counts, int nblk)
 {
     __shared__ uint32_t hist[SORT_RADIX];
     const int tid = threadIdx.x;
+    const int n = live_count(n_dev, cap);
     hist[tid] = 0;
     __syncthreads();
     const int start = blockIdx.x * SORT_CHUNK;
@@ -172,9 +186,11 @@ radix_rowscan_kernel(uint32_t* __restrict__ counts, int nblk, uint32_t* __restri
 
 __global__ void __launch_bounds__(256)
 radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                     uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift,
+                     uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                     const uint32_t* __restrict__ n_dev, int cap, int shift,
                      const uint32_t* __restrict__ counts, const uint32_t* __restrict__ totals, int nblk)
 {
+    const int n = live_count(n_dev, cap);
     __shared__ uint32_t digit_base[SORT_RADIX];      // next output slot of each digit for this block
     __shared__ uint32_t warp_cnt[2][8][SORT_RADIX];  // per-round per-warp digit counts -> offsets
     __shared__ uint32_t scan_tmp[8];
@@ -242,16 +258,19 @@ radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __res
 
 int sort_num_passes(int end_bit) { return (end_bit + SORT_RADIX_BITS - 1) / SORT_RADIX_BITS; }
 
-// Sorts n pairs.  Own sort: input must be in (keys_a, vals_a) when the pass count is even and in
-// (keys_b, vals_b) when it is odd; the result always lands in (keys_a, vals_a).  CUB: input in A,
-// *result_in_a tells where the result is.
-int launch_sort_pairs(int n, int end_bit, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b,
+// Sorts the first n pairs of arrays laid out for `cap` pairs; n = *n_dev (device) or, with n_dev == nullptr, cap.
+// Own sort: input must be in (keys_a, vals_a) when the pass count is even and in (keys_b, vals_b) when it is
+// odd; the result always lands in (keys_a, vals_a).  CUB (host-side count only): input in A, *result_in_a
+// tells where the result is.
+int launch_sort_pairs(const uint32_t* n_dev, int cap, int end_bit, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b,
                       uint32_t* vals_b, void* temp, size_t temp_bytes, bool use_cub, bool* result_in_a,
                       cudaStream_t s, bool debug)
 {
     *result_in_a = true;
+    const int n = cap;
     if (n <= 0) return SAGARS_OK;
     if (use_cub) {
+        if (n_dev != nullptr) { set_error("the CUB cross-check sort needs the host-side count"); return SAGARS_EINVAL; }
         cub::DoubleBuffer<uint64_t> dk(keys_a, keys_b);
         cub::DoubleBuffer<uint32_t> dv(vals_a, vals_b);
         size_t need = 0;
@@ -276,11 +295,11 @@ int launch_sort_pairs(int n, int end_bit, uint64_t* keys_a, uint32_t* vals_a, ui
     uint32_t* vout = (npass & 1) ? vals_a : vals_b;
     for (int p = 0; p < npass; p++) {
         const int shift = p * SORT_RADIX_BITS;
-        radix_hist_kernel<<<nblk, 256, 0, s>>>(kin, n, shift, counts, nblk);
+        radix_hist_kernel<<<nblk, 256, 0, s>>>(kin, n_dev, cap, shift, counts, nblk);
         SAGARS_LAUNCH_CHECK(s, debug);
         radix_rowscan_kernel<<<SORT_RADIX * 32 / 256, 256, 0, s>>>(counts, nblk, totals);
         SAGARS_LAUNCH_CHECK(s, debug);
-        radix_scatter_kernel<<<nblk, 256, 0, s>>>(kin, vin, kout, vout, n, shift, counts, totals, nblk);
+        radix_scatter_kernel<<<nblk, 256, 0, s>>>(kin, vin, kout, vout, n_dev, cap, shift, counts, totals, nblk);
         SAGARS_LAUNCH_CHECK(s, debug);
         uint64_t* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;
@@ -292,8 +311,9 @@ int launch_sort_pairs(int n, int end_bit, uint64_t* keys_a, uint32_t* vals_a, ui
 // tile ranges from the sorted keys (CF rasterizer_impl.cu:116-138)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-tile_ranges_kernel(int R, const uint64_t* __restrict__ keys, uint2* __restrict__ ranges)
+tile_ranges_kernel(const uint32_t* __restrict__ n_dev, int cap, const uint64_t* __restrict__ keys, uint2* __restrict__ ranges)
 {
+    const int R = live_count(n_dev, cap);
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= R) return;
     const uint32_t cur = (uint32_t)(keys[idx] >> 32);
@@ -309,11 +329,11 @@ tile_ranges_kernel(int R, const uint64_t* __restrict__ keys, uint2* __restrict__
     if (idx == R - 1) ranges[cur].y = (uint32_t)R;
 }
 
-int launch_tile_ranges(int R, int num_tiles, const uint64_t* keys, uint2* ranges, cudaStream_t s, bool debug)
+int launch_tile_ranges(const uint32_t* n_dev, int cap, int num_tiles, const uint64_t* keys, uint2* ranges, cudaStream_t s, bool debug)
 {
     SAGARS_CUDA(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), s));
-    if (R > 0) {
-        tile_ranges_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, keys, ranges);
+    if (cap > 0) {
+        tile_ranges_kernel<<<(cap + 255) / 256, 256, 0, s>>>(n_dev, cap, keys, ranges);
         SAGARS_LAUNCH_CHECK(s, debug);
     }
     return SAGARS_OK;

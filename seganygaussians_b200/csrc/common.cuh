@@ -186,13 +186,14 @@ struct Dims {
 
 int launch_preprocess(const sagars_forward_args& a, const Dims& d, GeomView g, cudaStream_t s, bool debug);
 int launch_scan_block_sums(const Dims& d, GeomView g, cudaStream_t s, bool debug);
+// n_dev / cap: element count in device memory (or nullptr: cap is the count) and the capacity of the arrays
 int launch_duplicate(const Dims& d, GeomView g, const int32_t* radii, uint64_t* keys, uint32_t* vals,
-                     cudaStream_t s, bool debug);
-int launch_sort_pairs(int n, int end_bit, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b,
+                     const uint32_t* n_dev, int cap, cudaStream_t s, bool debug);
+int launch_sort_pairs(const uint32_t* n_dev, int cap, int end_bit, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b,
                       uint32_t* vals_b, void* temp, size_t temp_bytes, bool use_cub, bool* result_in_a,
                       cudaStream_t s, bool debug);
 int sort_num_passes(int end_bit);
-int launch_tile_ranges(int R, int num_tiles, const uint64_t* keys, uint2* ranges, cudaStream_t s, bool debug);
+int launch_tile_ranges(const uint32_t* n_dev, int cap, int num_tiles, const uint64_t* keys, uint2* ranges, cudaStream_t s, bool debug);
 int launch_render_forward(const sagars_forward_args& a, const Dims& d, GeomView g, ImageView im,
                           const uint32_t* point_list, cudaStream_t s, bool debug);
 int launch_render_forward_tc(const sagars_forward_args& a, const Dims& d, GeomView g, ImageView im,

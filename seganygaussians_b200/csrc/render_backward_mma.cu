@@ -1,53 +1,52 @@
 // render_backward_mma.cu -- per-tile back-to-front gradient of the alpha compositing; the per-Gaussian reductions over
-// the tile's pixels are warp-level tensor-core GEMMs.
+// the tile's pixels are warp-level tensor-core GEMMs on COMPACTED rows.
 //
 // Semantics: CF cuda_rasterizer/backward.cu:399-559 (DEPTH backward.cu:400-564 adds dL_dmask), SURVEY.md Appendix
-// A.13-A.17 / D.  One CTA per 16x16 tile, one thread per pixel, splats taken back to front in batches of 16.
+// A.13-A.17 / D.  One CTA per 16x16 tile, one thread per pixel, splats taken back to front in staged batches of 32.
 //
 //   phase A (thread = pixel, the reference's traversal): four `power` tests at a time, one warp vote rejects splats no
-//     pixel of the warp can accept (conservative lower bound on power, math.cuh accept_threshold); accepted pairs
-//     recompute alpha, undo T and need ONE dot product s = f_j . g_p because the reference's per-channel recurrence
-//     accum_rec[ch] collapses to a scalar recurrence on a = accum_rec . g_p.  Each pair leaves two scalars in the
-//     warp's private operand tiles: W[j][p] = alpha*T (weight of dL/dcolour) and Q[j][p] = G * dL/dalpha (weight of
-//     every geometric gradient); everything else stays 0.
-//   phase B (per warp, no CTA barrier): the warp multiplies its own 16 x 32 tiles against the 32 gradient rows of
-//     its pixels and against the pixel-coordinate basis,
-//         dL/dcolour[j][:] += W[j][p] * g[p][:]                       (16 x 32 x C)
-//         moments[j][:]    += Q[j][p] * (1, x, y, x^2, xy, y^2)(p)    (16 x 32 x 8, tile-centred coordinates)
-//     with mma.sync.m16n8k8 TF32 in 3xTF32 split precision (~2^-21), accumulators in registers, and adds the result
-//     result in its own (now dead) operand slab.
-//   output (after the batch's CTA barrier): 16 threads per splat sum the warps' partial rows and turn them into ONE
-//     `red.global.add.v4.f32` per channel quad and six scalar reds (dL/dopacity, dL/dmean2D, dL/dconic in closed form
-//     from the six moments) -- instead of the reference's (C+6) atomics per blended (pixel, splat) pair.
+//     pixel of the warp's 8x4 block can accept (conservative lower bound on power, math.cuh accept_threshold).  Accepted
+//     pairs recompute alpha, undo T and need ONE dot product s = f_j . g_p because the reference's per-channel recurrence
+//     accum_rec[ch] collapses to a scalar recurrence on a = accum_rec . g_p.  A (warp, splat) instance with at least one
+//     candidate pixel appends ONE row to the warp's private ring: W[row][p] = alpha*T (weight of dL/dcolour) and
+//     Q[row][p] = G * dL/dalpha (weight of every geometric gradient), zero for the pixels that did not blend.  About 70 %
+//     of the (warp, splat) iterations append nothing.
+//   phase B (per warp, whenever 8 rows are waiting; no CTA barrier, no cross-warp traffic):
+//         dL/dcolour^T[:, row] = G^T (C x 32 pixels) * W^T (32 x 8 rows)           mma.sync m16n8k8 TF32, 3xTF32 split
+//         moments[row][:]      = Q (8 x 32) * (1, x, y, x^2, xy, y^2)(pixel)       tile-centred basis, exact in tf32
+//     accumulators in registers, results leave as fire-and-forget `red.global.add.f32`: C + 6 per (warp, splat) instance
+//     instead of the reference's C + 6 atomics per blended (pixel, splat) pair.  dL/dopacity, dL/dmean2D, dL/dconic follow
+//     in closed form from the six moments.
 //
-// Shared-memory rows are XOR/rotation swizzled instead of padded (g rows by quad, W/Q rows by 4 columns per row), which
-// makes both the thread-per-pixel float4 reads and the mma fragment gathers conflict-free and keeps 3 CTAs per SM.
+// The only CTA-wide synchronisation left is ONE barrier per staged batch (cp.async double buffer of records + feature
+// rows).  Shared-memory rows are rotation swizzled instead of padded (g rows by quad, ring rows by 4 columns per
+// sequence number), which keeps the thread-per-pixel float4 reads and the mma fragment gathers (nearly) conflict-free
+// and three CTAs per SM.
 #include "common.cuh"
 #include "cp_async.cuh"
 
 namespace sagars {
 
-constexpr int BM_NB = 16;   // instances per batch = M of the mma tiles
+constexpr int BM_NB = 32;     // splats per staged batch
+constexpr int BM_RING = 12;   // rows in a warp's ring (8 consumed per GEMM, at most 4 appended between checks)
+constexpr int BM_N = 8;       // rows per GEMM = N of the colour tiles = used M of the moment tile
 
 template <int NQ>
 struct BmCfg {
-    static constexpr int NQE = NQ < 2 ? 2 : NQ;     // quads per gradient row (>= 8 channels for one n-tile)
+    static constexpr int NQE = NQ < 2 ? 2 : NQ;     // quads per gradient row (power of two)
     static constexpr int ROW = 4 * NQE;             // floats per gradient row
-    static constexpr int NT = NQE / 2;              // 8-channel n-tiles
-    static constexpr int ACC_N = 8 * NT + 8;        // colour columns + 8 moment columns
-    static constexpr int SLAB = (BM_NB * ACC_N > 2 * BM_NB * 32) ? BM_NB * ACC_N : 2 * BM_NB * 32;   // floats per warp slab
+    static constexpr int MT = (ROW + 15) / 16;      // 16-channel m-tiles of the transposed colour product
 };
 
 template <int NQ>
 struct BmSmem {
     float Gs[TILE_PIX][BmCfg<NQ>::ROW];             // gradient rows by raster-local pixel; quad q of row r lives at quad (q + r) % NQE
-    // per-warp slab: operand tiles W[j][(lane + 4 j) & 31], Q[...] during phase A / the mma; after the mma the same 4 KB
-    // hold the warp's partial result P[16][ACC_N] until the CTA has summed the partials of all warps
-    float WQ[8][BmCfg<NQ>::SLAB];                   // W tile at [0, 512), Q tile at [512, 1024)
-    uint32_t touched[BM_NB];                        // splat had a blended pixel in this tile (this batch)
-    uint32_t contrib;                               // bit w: warp w left a partial result for this batch
-    float4 geo[2][BM_NB][2];                        // x, y, cx, cy | cz, opacity, accept_threshold, -
-    float4 feat[2][BM_NB][NQ];                      // feature rows, zero padded
+    float ringW[8][BM_RING][32];                    // per warp: row of sequence number s at s % RING, pixel p at (p + 4 s) & 31
+    float ringQ[8][BM_RING][32];
+    float4 ring_geo[8][BM_RING][2];                 // the appended splat's record (x, y, cx, cy | cz, opacity, -, -)
+    uint32_t ring_id[8][BM_RING];
+    float4 geo[2][BM_NB][2];                        // staged records: x, y, cx, cy | cz, opacity, accept_threshold, -
+    float4 feat[2][BM_NB][NQ];                      // staged feature rows, zero padded
     uint32_t ids[3][BM_NB];
     uint32_t max_contrib;
 };
@@ -64,31 +63,31 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo)
     lo = f2tf32(x - __uint_as_float(hi));
 }
 // D(16x8, f32) += A(16x8, tf32, row) * B(8x8, tf32, col)
-__device__ __forceinline__ void mma_16n8k8(float* d, const uint32_t* a, uint32_t b0, uint32_t b1)
+__device__ __forceinline__ void mma_16n8k8(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
 {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
 template <int NQ>
-__device__ __forceinline__ void bm_issue_batch(BmSmem<NQ>& sm, int gstage, int fstage, int idbuf, int cnt, int K, bool vec, bool color,
+__device__ __forceinline__ void bm_issue_batch(BmSmem<NQ>& sm, int stage, int idbuf, int cnt, int K, bool vec, bool color,
                                                const float* __restrict__ geo, const float* __restrict__ features)
 {
     const int tid = threadIdx.x;
     if (tid < cnt * 2) {
         const int j = tid >> 1, h = tid & 1;
-        cp_async16(&sm.geo[gstage][j][h], geo + 8 * (size_t)sm.ids[idbuf][j] + 4 * h);
+        cp_async16(&sm.geo[stage][j][h], geo + 8 * (size_t)sm.ids[idbuf][j] + 4 * h);
     }
     if (!color) return;
     if (vec) {
         const int nq = K >> 2;
         for (int c = tid; c < cnt * nq; c += TILE_PIX) {
             const int j = c / nq, q = c - j * nq;
-            cp_async16(&sm.feat[fstage][j][q], features + (size_t)sm.ids[idbuf][j] * K + 4 * q);
+            cp_async16(&sm.feat[stage][j][q], features + (size_t)sm.ids[idbuf][j] * K + 4 * q);
         }
     } else {
-        float* f = reinterpret_cast<float*>(&sm.feat[fstage][0][0]);
+        float* f = reinterpret_cast<float*>(&sm.feat[stage][0][0]);
         for (int c = tid; c < cnt * K; c += TILE_PIX) {
             const int j = c / K, k = c - j * K;
             f[j * (4 * NQ) + k] = features[(size_t)sm.ids[idbuf][j] * K + k];
@@ -97,17 +96,17 @@ __device__ __forceinline__ void bm_issue_batch(BmSmem<NQ>& sm, int gstage, int f
 }
 
 template <int NQ>
-__device__ __forceinline__ void bm_pad_geo(BmSmem<NQ>& sm, int gstage, int cnt)
+__device__ __forceinline__ void bm_pad_geo(BmSmem<NQ>& sm, int stage, int cnt)
 {
     const int tid = threadIdx.x;
     if (tid >= cnt && tid < BM_NB) {   // records past the end of the batch: never accepted (threshold = +inf)
-        sm.geo[gstage][tid][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        sm.geo[gstage][tid][1] = make_float4(0.f, 0.f, __int_as_float(0x7f800000), 0.f);
+        sm.geo[stage][tid][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        sm.geo[stage][tid][1] = make_float4(0.f, 0.f, __int_as_float(0x7f800000), 0.f);
     }
 }
 
 // NQ : float4 groups covering the gradient channels (K colour channels [+ 1 mask channel when MD])
-// VEC: K % 4 == 0 and no mask channel -> dL_dcolors rows are 16-byte aligned, use red.v4
+// VEC: K % 4 == 0 and no mask channel -> feature rows are 16-byte aligned, staged with cp.async
 template <int NQ, bool VEC, bool MD, bool COLOR>
 __global__ void __launch_bounds__(TILE_PIX, (NQ <= 8) ? 3 : 1)
 render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
@@ -119,7 +118,7 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
                            float* __restrict__ ggrad, float* __restrict__ dL_dcolors)
 {
     using Cfg = BmCfg<NQ>;
-    constexpr int NQE = Cfg::NQE, NT = Cfg::NT, ACC_N = Cfg::ACC_N;
+    constexpr int NQE = Cfg::NQE, ROW = Cfg::ROW, MT = Cfg::MT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BmSmem<NQ>& sm = *reinterpret_cast<BmSmem<NQ>*>(smem_raw);
 
@@ -142,12 +141,13 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
     const int my_n = inside ? (int)n_contrib[pix_id] : 0;
 
     // ---- one-time setup -------------------------------------------------------------------------------------------
-    if (tid == 0) { sm.max_contrib = 0; sm.contrib = 0; }
-    if (tid < BM_NB) sm.touched[tid] = 0;
-    {   // this warp's operand tiles start out zero
-        float4* w4 = reinterpret_cast<float4*>(&sm.WQ[warp][0]);
+    if (tid == 0) sm.max_contrib = 0;
+    {   // the ring starts out zero (rows past the fill level are multiplied too; their products are never used)
+        float* w = &sm.ringW[warp][0][0];
+        float* q = &sm.ringQ[warp][0][0];
 #pragma unroll
-        for (int i = 0; i < 8; i++) w4[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < BM_RING; i++) { w[i * 32 + lane] = 0.f; q[i * 32 + lane] = 0.f; }
+        if (lane < BM_RING) sm.ring_id[warp][lane] = 0;
     }
     if (!VEC || (K >> 2) < NQ) {   // zero the padded feature channels once
         float* f = reinterpret_cast<float*>(&sm.feat[0][0][0]);
@@ -193,7 +193,7 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
     // prologue: ids(0), ids(1); records + features of batch 0
     if (tid < batch_cnt(0)) sm.ids[0][tid] = load_id(0, tid);
     __syncthreads();
-    bm_issue_batch<NQ>(sm, 0, 0, 0, batch_cnt(0), K, VEC, COLOR, geo, features);
+    bm_issue_batch<NQ>(sm, 0, 0, batch_cnt(0), K, VEC, COLOR, geo, features);
     cp_async_commit();
     if (nbatch > 1 && tid < batch_cnt(1)) sm.ids[1][tid] = load_id(1, tid);
     cp_async_wait_all();
@@ -202,89 +202,138 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
 
     float T = T_final;
     float acc_r = 0.f, last_alpha = 0.f, last_s = 0.f;
-    bool dirty = false;   // this warp's operand tiles hold non-zero entries
+
+    // ring state (warp-uniform): rows [rseq, wseq) are waiting; physical row = sequence number % RING
+    int wseq = 0, rseq = 0, wrow = 0, rrow = 0;
+    float* const ringW = &sm.ringW[warp][0][0];
+    float* const ringQ = &sm.ringQ[warp][0][0];
 
     // mma fragment coordinates of this lane
     const int fg = lane >> 2, ft = lane & 3;
     const float half_W = 0.5f * (float)W, half_H = 0.5f * (float)H;   // (0.5 * W) rounded to float, as the reference
     const float tcx = (float)tile_x0 + 7.5f, tcy = (float)tile_y0 + 7.5f;
-    // partial results of all warps -> final sums of one batch -> global reductions (16 threads per splat)
-    auto flush_batch = [&](int pb) {
-        const int st = pb & 1, idb = pb % 3;
-        const int pcnt = batch_cnt(pb);
-        const int jj = tid >> 4, l16 = tid & 15;
-        const bool live = jj < pcnt && sm.touched[jj] != 0u;
-        const uint32_t cmask = sm.contrib;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);      // colour quad `l16` of splat jj
-        float4 mq = make_float4(0.f, 0.f, 0.f, 0.f);     // moment quad (lanes NQE and NQE+1 of the 16-lane group)
-        const int mh = (l16 == (NQE & 15)) ? 0 : (l16 == ((NQE + 1) & 15)) ? 1 : -1;
-        if (live) {
-            for (int w = 0; w < 8; w++) {
-                if (!((cmask >> w) & 1u)) continue;
-                const float* P = &sm.WQ[w][0] + jj * ACC_N;
-                if (l16 < NQE) {
-                    const float4 v = *reinterpret_cast<const float4*>(P + 4 * l16);
-                    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+
+    // multiply the waiting rows [rseq, rseq + nrows) (nrows <= 8) with the warp's gradient rows / the moment basis and
+    // send the results to global memory
+    auto flush_rows = [&](int nrows) {
+        __syncwarp();
+        float dc[MT][4];
+#pragma unroll
+        for (int m = 0; m < MT; m++) dc[m][0] = dc[m][1] = dc[m][2] = dc[m][3] = 0.f;
+        float dm[4] = {0.f, 0.f, 0.f, 0.f};
+        int rp = rrow + fg;                      // this lane's ring row: column n = fg of W^T, row fg of Q
+        if (rp >= BM_RING) rp -= BM_RING;
+        const int sw = 4 * ((rseq + fg) & 7);
+        const float* Wr = ringW + rp * 32;
+        const float* Qr = ringQ + rp * 32;
+#pragma unroll 1
+        for (int ks = 0; ks < 4; ks++) {
+            const int c0 = (ks * 8 + ft + sw) & 31, c1 = (c0 + 4) & 31;
+            uint32_t wh0, wl0, wh1, wl1, qh0, ql0, qh1, ql1;
+            split_tf32(Wr[c0], wh0, wl0);
+            split_tf32(Wr[c1], wh1, wl1);
+            split_tf32(Qr[c0], qh0, ql0);
+            split_tf32(Qr[c1], qh1, ql1);
+            // rows of the gradient tile: warp-local pixels ks*8 + ft and + 4  (same tile row, x and x+4)
+            const int r0 = ((warp >> 1) * 4 + ks) * TILE_X + (warp & 1) * 8 + ft;
+            const int r1 = r0 + 4;
+            if (COLOR || MD) {
+#pragma unroll
+                for (int m = 0; m < MT; m++) {
+                    const int cl = 16 * m + fg, chh = cl + 8;     // channels of fragment rows g and g + 8
+                    uint32_t ah[4], al[4];
+                    split_tf32(sm.Gs[r0][4 * (((cl >> 2) + r0) & (NQE - 1)) + (cl & 3)], ah[0], al[0]);
+                    split_tf32(sm.Gs[r1][4 * (((cl >> 2) + r1) & (NQE - 1)) + (cl & 3)], ah[2], al[2]);
+                    if (16 * m + 8 < ROW) {
+                        split_tf32(sm.Gs[r0][4 * (((chh >> 2) + r0) & (NQE - 1)) + (chh & 3)], ah[1], al[1]);
+                        split_tf32(sm.Gs[r1][4 * (((chh >> 2) + r1) & (NQE - 1)) + (chh & 3)], ah[3], al[3]);
+                    } else {
+                        ah[1] = al[1] = ah[3] = al[3] = 0u;
+                    }
+                    mma_16n8k8(dc[m], al[0], al[1], al[2], al[3], wh0, wh1);
+                    mma_16n8k8(dc[m], ah[0], ah[1], ah[2], ah[3], wl0, wl1);
+                    mma_16n8k8(dc[m], ah[0], ah[1], ah[2], ah[3], wh0, wh1);
                 }
-                if (mh >= 0) {
-                    const float4 v = *reinterpret_cast<const float4*>(P + 8 * NT + 4 * mh);
-                    mq.x += v.x; mq.y += v.y; mq.z += v.z; mq.w += v.w;
-                }
+            }
+            // B fragments of the moment basis X[p][m], p = warp-local pixel ks*8 + ft (+4), m = fg; exact in tf32
+            const float yb = (float)((warp >> 1) * 4 + ks) - 7.5f;
+            const float xb0 = (float)((warp & 1) * 8 + ft) - 7.5f, xb1 = xb0 + 4.f;
+            const float v0 = (fg == 0) ? 1.f : (fg == 1) ? xb0 : (fg == 2) ? yb : (fg == 3) ? xb0 * xb0 : (fg == 4) ? xb0 * yb : (fg == 5) ? yb * yb : 0.f;
+            const float v1 = (fg == 0) ? 1.f : (fg == 1) ? xb1 : (fg == 2) ? yb : (fg == 3) ? xb1 * xb1 : (fg == 4) ? xb1 * yb : (fg == 5) ? yb * yb : 0.f;
+            mma_16n8k8(dm, ql0, 0u, ql1, 0u, __float_as_uint(v0), __float_as_uint(v1));
+            mma_16n8k8(dm, qh0, 0u, qh1, 0u, __float_as_uint(v0), __float_as_uint(v1));
+        }
+
+        // colour product: this lane holds channels (16 m + fg, + 8) of rows 2 ft and 2 ft + 1
+        if (COLOR || MD) {
+            int ra = rrow + 2 * ft;
+            if (ra >= BM_RING) ra -= BM_RING;
+            int rb = ra + 1;
+            if (rb >= BM_RING) rb -= BM_RING;
+            const uint32_t ida = sm.ring_id[warp][ra], idb2 = sm.ring_id[warp][rb];
+            const bool va = 2 * ft < nrows, vb = 2 * ft + 1 < nrows;
+            auto emit = [&](uint32_t id, int ch, float v) {
+                if (COLOR && ch < K) red_add(dL_dcolors + (size_t)id * K + ch, v);
+                else if (MD && ch == K) red_add(ggrad + (size_t)id * GG_STRIDE + 6, v);
+            };
+#pragma unroll
+            for (int m = 0; m < MT; m++) {
+                const int cl = 16 * m + fg;
+                if (va) { emit(ida, cl, dc[m][0]); emit(ida, cl + 8, dc[m][2]); }
+                if (vb) { emit(idb2, cl, dc[m][1]); emit(idb2, cl + 8, dc[m][3]); }
             }
         }
-        const float m0 = __shfl_sync(0xffffffffu, mq.x, NQE & 15, 16);
-        const float mx = __shfl_sync(0xffffffffu, mq.y, NQE & 15, 16);
-        const float my = __shfl_sync(0xffffffffu, mq.z, NQE & 15, 16);
-        const float mxx = __shfl_sync(0xffffffffu, mq.w, NQE & 15, 16);
-        const float mxy = __shfl_sync(0xffffffffu, mq.x, (NQE + 1) & 15, 16);
-        const float myy = __shfl_sync(0xffffffffu, mq.y, (NQE + 1) & 15, 16);
-        if (live) {
-            const uint32_t id = sm.ids[idb][jj];
-            if (l16 < NQE) {
-                if (VEC) {
-                    if (4 * l16 < K) red_add_v4(dL_dcolors + (size_t)id * K + 4 * l16, a.x, a.y, a.z, a.w);
-                } else {
-                    const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        const int ch = 4 * l16 + c;
-                        if (COLOR && ch < K) red_add(dL_dcolors + (size_t)id * K + ch, av[c]);
-                        else if (MD && ch == K) red_add(ggrad + (size_t)id * GG_STRIDE + 6, av[c]);
-                    }
-                }
-            }
-            if (l16 < 6) {
-                const float4 g0 = sm.geo[st][jj][0];
-                const float4 g1 = sm.geo[st][jj][1];
+        // moments of row fg: (m0, mx) in lane ft = 0, (my, mxx) in ft = 1, (mxy, myy) in ft = 2 of the quad
+        {
+            const int q0 = lane & ~3;
+            const float m0 = __shfl_sync(0xffffffffu, dm[0], q0);
+            const float mx = __shfl_sync(0xffffffffu, dm[1], q0);
+            const float my = __shfl_sync(0xffffffffu, dm[0], q0 + 1);
+            const float mxx = __shfl_sync(0xffffffffu, dm[1], q0 + 1);
+            const float mxy = __shfl_sync(0xffffffffu, dm[0], q0 + 2);
+            const float myy = __shfl_sync(0xffffffffu, dm[1], q0 + 2);
+            if (fg < nrows && ft < 3) {
+                const float4 g0 = sm.ring_geo[warp][rp][0];
+                const float4 g1 = sm.ring_geo[warp][rp][1];
+                const uint32_t id = sm.ring_id[warp][rp];
                 const float conx = g0.z, cony = g0.w, conz = g1.x, o = g1.y;
                 // sums over the pixels of q * (1, dx, dy, dx^2, dx dy, dy^2) with d = centre - pixel = c - x'
                 const float cx = g0.x - tcx, cy = g0.y - tcy;
                 const float Sx = cx * m0 - mx;
                 const float Sy = cy * m0 - my;
-                const float Sxx = cx * cx * m0 - 2.f * cx * mx + mxx;
-                const float Sxy = cx * cy * m0 - cx * my - cy * mx + mxy;
-                const float Syy = cy * cy * m0 - 2.f * cy * my + myy;
-                float v;
-                int slot;
-                if (l16 == 0) { v = m0; slot = 5; }                                           // dL/dopacity
-                else if (l16 == 1) { v = -o * half_W * (conx * Sx + cony * Sy); slot = 0; }   // dL/dmean2D.x
-                else if (l16 == 2) { v = -o * half_H * (conz * Sy + cony * Sx); slot = 1; }   // dL/dmean2D.y
-                else if (l16 == 3) { v = -0.5f * o * Sxx; slot = 2; }                         // dL/dconic.x
-                else if (l16 == 4) { v = -0.5f * o * Sxy; slot = 3; }                         // dL/dconic.y
-                else { v = -0.5f * o * Syy; slot = 4; }                                       // dL/dconic.w
-                red_add(ggrad + (size_t)id * GG_STRIDE + slot, v);
+                float ua, ub;
+                int sa, sb;
+                if (ft == 0) {
+                    ua = m0; sa = 5;                                                  // dL/dopacity
+                    ub = -o * half_W * (conx * Sx + cony * Sy); sb = 0;               // dL/dmean2D.x
+                } else if (ft == 1) {
+                    const float Sxx = cx * cx * m0 - 2.f * cx * mx + mxx;
+                    ua = -o * half_H * (conz * Sy + cony * Sx); sa = 1;               // dL/dmean2D.y
+                    ub = -0.5f * o * Sxx; sb = 2;                                     // dL/dconic.x
+                } else {
+                    const float Sxy = cx * cy * m0 - cx * my - cy * mx + mxy;
+                    const float Syy = cy * cy * m0 - 2.f * cy * my + myy;
+                    ua = -0.5f * o * Sxy; sa = 3;                                     // dL/dconic.y
+                    ub = -0.5f * o * Syy; sb = 4;                                     // dL/dconic.w
+                }
+                red_add(ggrad + (size_t)id * GG_STRIDE + sa, ua);
+                red_add(ggrad + (size_t)id * GG_STRIDE + sb, ub);
             }
         }
+        rseq += nrows;
+        rrow += nrows;
+        if (rrow >= BM_RING) rrow -= BM_RING;
+        __syncwarp();   // every lane is done with the rows before they are overwritten
     };
 
     for (int b = 0; b < nbatch; b++) {
-        const int fstage = b & 1, gstage = b & 1;
+        const int stage = b & 1, idb = b % 3;
         const int cnt = batch_cnt(b);
         const int pos_hi = maxc - 1 - b * BM_NB;
 
         // data of batch b+1 starts flying; ids of batch b+2 into a register
         if (b + 1 < nbatch) {
-            bm_issue_batch<NQ>(sm, gstage ^ 1, fstage ^ 1, (b + 1) % 3, batch_cnt(b + 1), K, VEC, COLOR, geo, features);
+            bm_issue_batch<NQ>(sm, stage ^ 1, (b + 1) % 3, batch_cnt(b + 1), K, VEC, COLOR, geo, features);
             cp_async_commit();
         }
         uint32_t next_id = 0;
@@ -292,23 +341,15 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
         if (have_next_id) next_id = load_id(b + 2, tid);
 
         // ---------------- phase A: thread = pixel ----------------
-        bool warp_any = false;
         if (pos_hi - (cnt - 1) < warp_n) {   // some pixel of this warp still has contributors in this batch
-            if (dirty) {   // the slab still holds last batch's operands / partial result
-                float4* w4 = reinterpret_cast<float4*>(&sm.WQ[warp][0]);
-#pragma unroll
-                for (int i = 0; i < 8; i++) w4[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                dirty = false;
-                __syncwarp();
-            }
             for (int j0 = 0; j0 < cnt; j0 += 4) {
                 if (pos_hi - (j0 + 3) >= warp_n) continue;                              // warp-uniform
                 float pw[4], op[4];
                 bool cd[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const float4 g0 = sm.geo[gstage][j0 + i][0];
-                    const float4 g1 = sm.geo[gstage][j0 + i][1];
+                    const float4 g0 = sm.geo[stage][j0 + i][0];
+                    const float4 g1 = sm.geo[stage][j0 + i][1];
                     const float dx = g0.x - pixx, dy = g0.y - pixy;
                     pw[i] = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
                     cd[i] = (pos_hi - (j0 + i) < my_n) && !(pw[i] > 0.0f) && (pw[i] >= g1.z);
@@ -319,7 +360,7 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
                 for (int i = 0; i < 4; i++) {
                     if (!__any_sync(0xffffffffu, cd[i])) continue;                      // warp-uniform
                     const int jj = j0 + i;
-                    bool blended = false;
+                    float w = 0.f, q = 0.f;
                     if (cd[i]) {
                         const float G = expf(pw[i]);
                         const float alpha = fminf(0.99f, op[i] * G);
@@ -329,9 +370,9 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
                             if (COLOR) {
                                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                                for (int q = 0; q < NQ; q++) {
-                                    const float4 f = sm.feat[fstage][jj][q];
-                                    const float4 gv = *reinterpret_cast<const float4*>(&sm.Gs[rl][4 * ((q + rl) & (NQE - 1))]);
+                                for (int qd = 0; qd < NQ; qd++) {
+                                    const float4 f = sm.feat[stage][jj][qd];
+                                    const float4 gv = *reinterpret_cast<const float4*>(&sm.Gs[rl][4 * ((qd + rl) & (NQE - 1))]);
                                     s0 += f.x * gv.x;
                                     s1 += f.y * gv.y;
                                     s2 += f.z * gv.z;
@@ -344,85 +385,30 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
                             float dL_dalpha = (s - acc_r) * T;
                             last_alpha = alpha;
                             dL_dalpha += (-T_final / (1.f - alpha)) * bgdot;
-                            const int col = (lane + 4 * jj) & 31;
-                            sm.WQ[warp][jj * 32 + col] = alpha * T;
-                            sm.WQ[warp][512 + jj * 32 + col] = G * dL_dalpha;
-                            blended = true;
+                            w = alpha * T;
+                            q = G * dL_dalpha;
                         }
                     }
-                    if (__any_sync(0xffffffffu, blended)) {
-                        warp_any = true;
-                        if (lane == 0) sm.touched[jj] = 1u;
-                    }
+                    // append one row (all lanes write: zero where the pixel did not blend)
+                    const int col = (lane + 4 * (wseq & 7)) & 31;
+                    ringW[wrow * 32 + col] = w;
+                    ringQ[wrow * 32 + col] = q;
+                    if (lane < 2) sm.ring_geo[warp][wrow][lane] = sm.geo[stage][jj][lane];
+                    if (lane == 2) sm.ring_id[warp][wrow] = sm.ids[idb][jj];
+                    wseq++;
+                    wrow = (wrow == BM_RING - 1) ? 0 : wrow + 1;
                 }
+                if (wseq - rseq >= BM_N) flush_rows(BM_N);
             }
-        }
-
-        // ---------------- phase B: this warp's 16 x 32 tiles times its 32 gradient rows / the moment basis ----------------
-        if (warp_any) {
-            dirty = true;
-            __syncwarp();
-            float d[NT + 1][4];
-#pragma unroll
-            for (int n = 0; n <= NT; n++) d[n][0] = d[n][1] = d[n][2] = d[n][3] = 0.f;
-            const float* Wt = &sm.WQ[warp][0];
-            const float* Qt = &sm.WQ[warp][512];
-#pragma unroll 1
-            for (int ks = 0; ks < 4; ks++) {
-                const int c0 = (ks * 8 + ft + 4 * fg) & 31, c1 = (ks * 8 + ft + 4 + 4 * fg) & 31;
-                uint32_t awh[4], awl[4], aqh[4], aql[4];
-                split_tf32(Wt[fg * 32 + c0], awh[0], awl[0]);
-                split_tf32(Wt[(fg + 8) * 32 + c0], awh[1], awl[1]);
-                split_tf32(Wt[fg * 32 + c1], awh[2], awl[2]);
-                split_tf32(Wt[(fg + 8) * 32 + c1], awh[3], awl[3]);
-                split_tf32(Qt[fg * 32 + c0], aqh[0], aql[0]);
-                split_tf32(Qt[(fg + 8) * 32 + c0], aqh[1], aql[1]);
-                split_tf32(Qt[fg * 32 + c1], aqh[2], aql[2]);
-                split_tf32(Qt[(fg + 8) * 32 + c1], aqh[3], aql[3]);
-                // rows of the gradient tile: warp-local pixels ks*8 + ft and + 4  (same tile row, x and x+4)
-                const int r0 = ((warp >> 1) * 4 + ks) * TILE_X + (warp & 1) * 8 + ft;
-                const int r1 = r0 + 4;
-#pragma unroll
-                for (int n = 0; n < NT; n++) {
-                    const int ch = 8 * n + fg;
-                    const float b0f = sm.Gs[r0][4 * (((ch >> 2) + r0) & (NQE - 1)) + (ch & 3)];
-                    const float b1f = sm.Gs[r1][4 * (((ch >> 2) + r1) & (NQE - 1)) + (ch & 3)];
-                    uint32_t b0h, b0l, b1h, b1l;
-                    split_tf32(b0f, b0h, b0l);
-                    split_tf32(b1f, b1h, b1l);
-                    mma_16n8k8(d[n], awl, b0h, b1h);
-                    mma_16n8k8(d[n], awh, b0l, b1l);
-                    mma_16n8k8(d[n], awh, b0h, b1h);
-                }
-                // B fragments of the moment basis X[p][m], p = warp-local pixel ks*8 + ft (+4), m = fg; exact in tf32
-                const float yb = (float)((warp >> 1) * 4 + ks) - 7.5f;
-                const float xb0 = (float)((warp & 1) * 8 + ft) - 7.5f, xb1 = xb0 + 4.f;
-                const float v0 = (fg == 0) ? 1.f : (fg == 1) ? xb0 : (fg == 2) ? yb : (fg == 3) ? xb0 * xb0 : (fg == 4) ? xb0 * yb : (fg == 5) ? yb * yb : 0.f;
-                const float v1 = (fg == 0) ? 1.f : (fg == 1) ? xb1 : (fg == 2) ? yb : (fg == 3) ? xb1 * xb1 : (fg == 4) ? xb1 * yb : (fg == 5) ? yb * yb : 0.f;
-                mma_16n8k8(d[NT], aql, __float_as_uint(v0), __float_as_uint(v1));
-                mma_16n8k8(d[NT], aqh, __float_as_uint(v0), __float_as_uint(v1));
-            }
-            // the operand tiles are dead now: the slab takes the warp's partial result P[16][ACC_N]
-            __syncwarp();
-            float* P = &sm.WQ[warp][0];
-#pragma unroll
-            for (int n = 0; n <= NT; n++) {
-                *reinterpret_cast<float2*>(P + fg * ACC_N + 8 * n + 2 * ft) = make_float2(d[n][0], d[n][1]);
-                *reinterpret_cast<float2*>(P + (fg + 8) * ACC_N + 8 * n + 2 * ft) = make_float2(d[n][2], d[n][3]);
-            }
-            if (lane == 0) atomicOr(&sm.contrib, 1u << warp);
         }
 
         // publish ids(b+2); wait for the copies of batch b+1
         if (have_next_id) sm.ids[(b + 2) % 3][tid] = next_id;
         cp_async_wait_all();
-        if (b + 1 < nbatch) bm_pad_geo<NQ>(sm, gstage ^ 1, batch_cnt(b + 1));
-        __syncthreads();         // all partial results of batch b are in the slabs (the imbalanced part ends here)
-        flush_batch(b);          // sum them, one global reduction per (splat, quad) + six per splat
-        __syncthreads();         // slabs may be rewritten (short, balanced section between the two barriers)
-        if (tid < BM_NB) sm.touched[tid] = 0;
-        if (tid == BM_NB) sm.contrib = 0;
+        if (b + 1 < nbatch) bm_pad_geo<NQ>(sm, stage ^ 1, batch_cnt(b + 1));
+        __syncthreads();   // batch b+1 is visible; nobody reads the buffers of batch b any more
     }
+    if (wseq - rseq > 0) flush_rows(wseq - rseq);
 }
 
 template <int NQ, bool VEC, bool MD, bool COLOR>

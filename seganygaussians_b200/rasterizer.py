@@ -105,6 +105,20 @@ def _flags(settings: GaussianRasterizationSettings, extra: int = 0) -> int:
 
 _USE_CUB_SORT = False
 _USE_TENSOR_CORES = True
+_SPECULATIVE_BINNING = True
+# (device index, P, W, H) -> largest instance count seen so far: the next forward of that shape asks for a binning
+# buffer 25 % larger than this BEFORE the count is known (include/sagars.h, `binning_capacity_hint`)
+_CAPACITY_SEEN: dict = {}
+# capacity the binning buffer of the most recent forward was laid out for (tests decode the scratch with it)
+last_binning_capacity = 0
+
+
+def set_speculative_binning(enabled: bool) -> None:
+    """Queue sort / ranges / blend behind a capacity guess instead of waiting for the instance count (default on).
+    Off: the reference's order -- read the count back, then size the binning buffer exactly."""
+    global _SPECULATIVE_BINNING
+    _SPECULATIVE_BINNING = bool(enabled)
+    _CAPACITY_SEEN.clear()
 
 
 def set_tensor_cores(enabled: bool) -> None:
@@ -202,6 +216,11 @@ def _forward_impl(settings, variant_flags, default_channels, means3D, sh, colors
         a.out_mask = _ptr(out_mask)
         a.out_depth = _ptr(out_depth)
         a.radii = _ptr(radii)
+        cap_key = (a.device, P, W, H)
+        seen = _CAPACITY_SEEN.get(cap_key, 0) if _SPECULATIVE_BINNING else 0
+        a.binning_capacity_hint = min(seen + seen // 4 + 4096, 2**31 - 1) if seen > 0 else 0
+        cap_out = C.c_int32(0)
+        a.binning_capacity_out = C.pointer(cap_out)
 
         scratch = _Scratch(device)
         num_rendered = C.c_int32(0)
@@ -210,6 +229,10 @@ def _forward_impl(settings, variant_flags, default_channels, means3D, sh, colors
         if scratch.error is not None:
             raise scratch.error
         _lib.check(rc)
+        global last_binning_capacity
+        last_binning_capacity = int(cap_out.value)
+        if _SPECULATIVE_BINNING and num_rendered.value > seen:
+            _CAPACITY_SEEN[cap_key] = int(num_rendered.value)
         geom, binning, img = scratch.buffers
         if binning is None:
             binning = torch.empty(0, dtype=torch.uint8, device=device)

@@ -123,6 +123,9 @@ def run_torch_impl(kind: str, sc, K: int, depth: bool = False, use_sh: bool = Fa
     saved = ctx.saved_tensors
     geom, binning, img = saved[-3], saved[-2], saved[-1]
     o.num_rendered = int(ctx.num_rendered)
+    if kind == "ours":
+        from seganygaussians_b200 import rasterizer as _R
+        o.binning_capacity = int(_R.last_binning_capacity)
     _decode(o, kind, sc, geom, binning, img)
     if backward:
         loss = (color * sc.dL_dout[:K].to(dev)).sum()
@@ -155,7 +158,8 @@ def _decode(o, kind, sc, geom, binning, img):
     N = H * W
     if kind == "ours":
         from seganygaussians_b200 import _lib
-        gl, il, bl = _lib.geom_layout(P), _lib.image_layout(W, H), _lib.binning_layout(R)
+        # the binning arrays are laid out for the capacity the forward asked for (>= R with speculative binning)
+        gl, il, bl = _lib.geom_layout(P), _lib.image_layout(W, H), _lib.binning_layout(getattr(o, "binning_capacity", R))
         o.tiles_touched = _bytes_view(geom, gl.tiles_touched, np.uint32, P)
         o.point_offsets = _bytes_view(geom, gl.point_offsets, np.uint32, P)
         geo = _bytes_view(geom, gl.geo, np.float32, P * 8).reshape(P, 8)

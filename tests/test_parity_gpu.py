@@ -237,3 +237,31 @@ def test_mask_only_path_matches_depth_variant_mask():
     (out_mask * gm).sum().backward()
     (mask_only * gm).sum().backward()
     assert torch.allclose(m1.grad, m2.grad, rtol=1e-4, atol=1e-9)
+
+
+def test_speculative_binning_matches_exact_layout():
+    """The capacity-hint path (include/sagars.h `binning_capacity_hint`): exact layout, a generous hint and a hint that
+    is too small (stages skipped on the device, then re-issued) must all give identical integer state and images."""
+    from seganygaussians_b200 import rasterizer as R
+    sc = synthetic.scene(4000, 88, 120, 32)
+    key = (0, sc.P, sc.W, sc.H)
+    try:
+        R.set_speculative_binning(False)
+        exact = common.run_torch_impl("ours", sc, 32)
+        assert exact.binning_capacity == exact.num_rendered
+        R.set_speculative_binning(True)
+        first = common.run_torch_impl("ours", sc, 32)             # nothing seen yet for this shape: exact layout
+        assert first.binning_capacity == first.num_rendered
+        roomy = common.run_torch_impl("ours", sc, 32)             # hint = 1.25 x seen
+        assert roomy.binning_capacity > roomy.num_rendered
+        R._CAPACITY_SEEN[key] = max(1, exact.num_rendered // 3)   # force an overflow
+        small = common.run_torch_impl("ours", sc, 32)
+        assert small.binning_capacity == small.num_rendered       # re-issued with the exact size
+        R._CAPACITY_SEEN[key] = 10 * exact.num_rendered           # far too large is fine as well
+        huge = common.run_torch_impl("ours", sc, 32)
+    finally:
+        R.set_speculative_binning(True)
+    for other in (first, roomy, small, huge):
+        ok, report = common.compare(other, exact, ints=common.INT_FWD + ("keys",), floats=common.FLOAT_FWD + common.GRADS)
+        assert ok, report
+        assert np.array_equal(other.color, exact.color)
