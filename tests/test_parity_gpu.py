@@ -125,8 +125,9 @@ def test_full_size_properties():
     sc = synthetic.scene(P, H, W, K)
     ones = torch.ones(P, K)
     col, radii, (R_, geom, binning, img) = _render(sc, K, colors=ones)
-    from seganygaussians_b200 import _lib
-    il, bl, gl = _lib.image_layout(W, H), _lib.binning_layout(R_), _lib.geom_layout(P)
+    from seganygaussians_b200 import _lib, rasterizer as R
+    # the binning arrays are laid out for the capacity the forward asked for (>= R_ with speculative binning)
+    il, bl, gl = _lib.image_layout(W, H), _lib.binning_layout(R.last_binning_capacity), _lib.geom_layout(P)
     final_T = img[il.final_T: il.final_T + 4 * H * W].view(torch.float32).view(H, W).cpu()
     # X5 partition of unity: features == 1, bg == 0  ->  out == 1 - final_T on every channel
     assert torch.allclose(col[0], 1.0 - final_T, rtol=0, atol=3e-6) and torch.equal(col[0], col[K - 1])
