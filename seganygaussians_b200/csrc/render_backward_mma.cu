@@ -2,15 +2,16 @@
 // the tile's pixels are warp-level tensor-core GEMMs on COMPACTED rows.
 //
 // Semantics: CF cuda_rasterizer/backward.cu:399-559 (DEPTH backward.cu:400-564 adds dL_dmask), SURVEY.md Appendix
-// A.13-A.17 / D.  One CTA per 16x16 tile, one thread per pixel, splats taken back to front in staged batches of 32.
+// A.13-A.17 / D.  One CTA per 16x16 tile, one thread per pixel, splats taken back to front in staged batches of 64.
 //
-//   phase A (thread = pixel, the reference's traversal): four `power` tests at a time, one warp vote rejects splats no
-//     pixel of the warp's 8x4 block can accept (conservative lower bound on power, math.cuh accept_threshold).  Accepted
-//     pairs recompute alpha, undo T and need ONE dot product s = f_j . g_p because the reference's per-channel recurrence
-//     accum_rec[ch] collapses to a scalar recurrence on a = accum_rec . g_p.  A (warp, splat) instance with at least one
-//     candidate pixel appends ONE row to the warp's private ring: W[row][p] = alpha*T (weight of dL/dcolour) and
-//     Q[row][p] = G * dL/dalpha (weight of every geometric gradient), zero for the pixels that did not blend.  About 70 %
-//     of the (warp, splat) iterations append nothing.
+//   phase A: first, lane = splat: 32 splats at a time are tested against the warp's 8x4 pixel block (exact minimum of
+//     the splat's quadratic form over the block vs. the conservative accept threshold of math.cuh) -- about 70 % of the
+//     (warp, splat) pairs end here, 32 per instruction.  Then thread = pixel over the surviving splats (the
+//     reference's traversal): accepted pairs recompute alpha, undo T and need ONE dot product s = f_j . g_p because the
+//     reference's per-channel recurrence accum_rec[ch] collapses to a scalar recurrence on a = accum_rec . g_p.  A
+//     (warp, splat) instance with at least one accepted pixel appends ONE row to the warp's private tiles:
+//     W[row][p] = alpha*T (weight of dL/dcolour) and Q[row][p] = G * dL/dalpha (weight of every geometric gradient),
+//     zero for the pixels that did not blend.
 //   phase B (per warp, whenever 8 rows are waiting; no CTA barrier, no cross-warp traffic):
 //         dL/dcolour^T[:, row] = G^T (C x 32 pixels) * W^T (32 x 8 rows)           mma.sync m16n8k8 TF32, 3xTF32 split
 //         moments[row][:]      = Q (8 x 32) * (1, x, y, x^2, xy, y^2)(pixel)       tile-centred basis, exact in tf32
@@ -19,17 +20,16 @@
 //     in closed form from the six moments.
 //
 // The only CTA-wide synchronisation left is ONE barrier per staged batch (cp.async double buffer of records + feature
-// rows).  Shared-memory rows are rotation swizzled instead of padded (g rows by quad, ring rows by 4 columns per
-// sequence number), which keeps the thread-per-pixel float4 reads and the mma fragment gathers (nearly) conflict-free
+// rows).  Shared-memory rows are rotation swizzled instead of padded (g rows by quad, operand rows by 4 columns per
+// row), which keeps the thread-per-pixel float4 reads and the mma fragment gathers (nearly) conflict-free
 // and three CTAs per SM.
 #include "common.cuh"
 #include "cp_async.cuh"
 
 namespace sagars {
 
-constexpr int BM_NB = 32;     // splats per staged batch
-constexpr int BM_RING = 12;   // rows in a warp's ring (8 consumed per GEMM, at most 4 appended between checks)
-constexpr int BM_N = 8;       // rows per GEMM = N of the colour tiles = used M of the moment tile
+constexpr int BM_NB = 64;     // splats per staged batch (two 32-wide candidate masks per warp)
+constexpr int BM_N = 8;       // rows a warp collects per GEMM = N of the colour tiles = used M of the moment tile
 
 template <int NQ>
 struct BmCfg {
@@ -41,10 +41,9 @@ struct BmCfg {
 template <int NQ>
 struct BmSmem {
     float Gs[TILE_PIX][BmCfg<NQ>::ROW];             // gradient rows by raster-local pixel; quad q of row r lives at quad (q + r) % NQE
-    float ringW[8][BM_RING][32];                    // per warp: row of sequence number s at s % RING, pixel p at (p + 4 s) & 31
-    float ringQ[8][BM_RING][32];
-    float4 ring_geo[8][BM_RING][2];                 // the appended splat's record (x, y, cx, cy | cz, opacity, -, -)
-    uint32_t ring_id[8][BM_RING];
+    float rowW[8][BM_N][32];                        // per warp: row r, pixel p at (p + 4 r) & 31
+    float rowQ[8][BM_N][32];
+    uint32_t row_id[8][BM_N];                       // Gaussian index of the row
     float4 geo[2][BM_NB][2];                        // staged records: x, y, cx, cy | cz, opacity, accept_threshold, -
     float4 feat[2][BM_NB][NQ];                      // staged feature rows, zero padded
     uint32_t ids[3][BM_NB];
@@ -57,10 +56,12 @@ __device__ __forceinline__ uint32_t f2tf32(float x)
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
+// x = hi + lo with hi exact in tf32 (truncation) and lo = x - hi exact in fp32; the tensor core reads the top 19 bits
+// of lo, so hi*hi' + hi*lo' + lo*hi' carries ~2^-21 relative error (cvt.rna.tf32 would cost ~5 instructions each)
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo)
 {
-    hi = f2tf32(x);
-    lo = f2tf32(x - __uint_as_float(hi));
+    hi = __float_as_uint(x) & 0xFFFFE000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
 }
 // D(16x8, f32) += A(16x8, tf32, row) * B(8x8, tf32, col)
 __device__ __forceinline__ void mma_16n8k8(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
@@ -142,12 +143,12 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
 
     // ---- one-time setup -------------------------------------------------------------------------------------------
     if (tid == 0) sm.max_contrib = 0;
-    {   // the ring starts out zero (rows past the fill level are multiplied too; their products are never used)
-        float* w = &sm.ringW[warp][0][0];
-        float* q = &sm.ringQ[warp][0][0];
+    {   // rows past the fill level are multiplied too (their products are never used): start from finite values
+        float* w = &sm.rowW[warp][0][0];
+        float* q = &sm.rowQ[warp][0][0];
 #pragma unroll
-        for (int i = 0; i < BM_RING; i++) { w[i * 32 + lane] = 0.f; q[i * 32 + lane] = 0.f; }
-        if (lane < BM_RING) sm.ring_id[warp][lane] = 0;
+        for (int i = 0; i < BM_N; i++) { w[i * 32 + lane] = 0.f; q[i * 32 + lane] = 0.f; }
+        if (lane < BM_N) sm.row_id[warp][lane] = 0;
     }
     if (!VEC || (K >> 2) < NQ) {   // zero the padded feature channels once
         float* f = reinterpret_cast<float*>(&sm.feat[0][0][0]);
@@ -203,32 +204,39 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
     float T = T_final;
     float acc_r = 0.f, last_alpha = 0.f, last_s = 0.f;
 
-    // ring state (warp-uniform): rows [rseq, wseq) are waiting; physical row = sequence number % RING
-    int wseq = 0, rseq = 0, wrow = 0, rrow = 0;
-    float* const ringW = &sm.ringW[warp][0][0];
-    float* const ringQ = &sm.ringQ[warp][0][0];
+    int nrow = 0;   // rows waiting in this warp's tiles (warp-uniform)
+    float* const rowW = &sm.rowW[warp][0][0];
+    float* const rowQ = &sm.rowQ[warp][0][0];
 
     // mma fragment coordinates of this lane
     const int fg = lane >> 2, ft = lane & 3;
     const float half_W = 0.5f * (float)W, half_H = 0.5f * (float)H;   // (0.5 * W) rounded to float, as the reference
     const float tcx = (float)tile_x0 + 7.5f, tcy = (float)tile_y0 + 7.5f;
+    // the warp's 8x4 pixel block (pixel centres), for the block-level candidate test
+    const float bx0 = (float)(tile_x0 + (warp & 1) * 8), bx1 = bx0 + 7.f;
+    const float by0 = (float)(tile_y0 + (warp >> 1) * 4), by1 = by0 + 3.f;
 
-    // multiply the waiting rows [rseq, rseq + nrows) (nrows <= 8) with the warp's gradient rows / the moment basis and
-    // send the results to global memory
+    // multiply the waiting rows [0, nrows) (nrows <= 8) with the warp's gradient rows / the moment basis and send the
+    // results to global memory
     auto flush_rows = [&](int nrows) {
         __syncwarp();
         float dc[MT][4];
 #pragma unroll
         for (int m = 0; m < MT; m++) dc[m][0] = dc[m][1] = dc[m][2] = dc[m][3] = 0.f;
         float dm[4] = {0.f, 0.f, 0.f, 0.f};
-        int rp = rrow + fg;                      // this lane's ring row: column n = fg of W^T, row fg of Q
-        if (rp >= BM_RING) rp -= BM_RING;
-        const int sw = 4 * ((rseq + fg) & 7);
-        const float* Wr = ringW + rp * 32;
-        const float* Qr = ringQ + rp * 32;
+        // this lane's row of the tiles: column n = fg of W^T, row fg of Q; pixel p sits at column (p + 4 fg) & 31
+        const float* Wr = rowW + fg * 32;
+        const float* Qr = rowQ + fg * 32;
+        // moment basis X[p][m] of fragment column m = fg at pixel (x, y): value = xa + (xb + xc * y) * y
+        const float x0 = (float)((warp & 1) * 8 + ft) - 7.5f, x1 = x0 + 4.f;
+        const float xa0 = (fg == 0) ? 1.f : (fg == 1) ? x0 : (fg == 3) ? x0 * x0 : 0.f;
+        const float xa1 = (fg == 0) ? 1.f : (fg == 1) ? x1 : (fg == 3) ? x1 * x1 : 0.f;
+        const float xb0 = (fg == 2) ? 1.f : (fg == 4) ? x0 : 0.f;
+        const float xb1 = (fg == 2) ? 1.f : (fg == 4) ? x1 : 0.f;
+        const float xc = (fg == 5) ? 1.f : 0.f;
 #pragma unroll 1
         for (int ks = 0; ks < 4; ks++) {
-            const int c0 = (ks * 8 + ft + sw) & 31, c1 = (c0 + 4) & 31;
+            const int c0 = (ks * 8 + ft + 4 * fg) & 31, c1 = (c0 + 4) & 31;
             uint32_t wh0, wl0, wh1, wl1, qh0, ql0, qh1, ql1;
             split_tf32(Wr[c0], wh0, wl0);
             split_tf32(Wr[c1], wh1, wl1);
@@ -255,22 +263,17 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
                     mma_16n8k8(dc[m], ah[0], ah[1], ah[2], ah[3], wh0, wh1);
                 }
             }
-            // B fragments of the moment basis X[p][m], p = warp-local pixel ks*8 + ft (+4), m = fg; exact in tf32
+            // B fragments of the moment basis, p = warp-local pixel ks*8 + ft (+4); exact in tf32
             const float yb = (float)((warp >> 1) * 4 + ks) - 7.5f;
-            const float xb0 = (float)((warp & 1) * 8 + ft) - 7.5f, xb1 = xb0 + 4.f;
-            const float v0 = (fg == 0) ? 1.f : (fg == 1) ? xb0 : (fg == 2) ? yb : (fg == 3) ? xb0 * xb0 : (fg == 4) ? xb0 * yb : (fg == 5) ? yb * yb : 0.f;
-            const float v1 = (fg == 0) ? 1.f : (fg == 1) ? xb1 : (fg == 2) ? yb : (fg == 3) ? xb1 * xb1 : (fg == 4) ? xb1 * yb : (fg == 5) ? yb * yb : 0.f;
+            const float v0 = xa0 + (xb0 + xc * yb) * yb;
+            const float v1 = xa1 + (xb1 + xc * yb) * yb;
             mma_16n8k8(dm, ql0, 0u, ql1, 0u, __float_as_uint(v0), __float_as_uint(v1));
             mma_16n8k8(dm, qh0, 0u, qh1, 0u, __float_as_uint(v0), __float_as_uint(v1));
         }
 
         // colour product: this lane holds channels (16 m + fg, + 8) of rows 2 ft and 2 ft + 1
         if (COLOR || MD) {
-            int ra = rrow + 2 * ft;
-            if (ra >= BM_RING) ra -= BM_RING;
-            int rb = ra + 1;
-            if (rb >= BM_RING) rb -= BM_RING;
-            const uint32_t ida = sm.ring_id[warp][ra], idb2 = sm.ring_id[warp][rb];
+            const uint32_t ida = sm.row_id[warp][2 * ft], idb2 = sm.row_id[warp][2 * ft + 1];
             const bool va = 2 * ft < nrows, vb = 2 * ft + 1 < nrows;
             auto emit = [&](uint32_t id, int ch, float v) {
                 if (COLOR && ch < K) red_add(dL_dcolors + (size_t)id * K + ch, v);
@@ -293,9 +296,9 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
             const float mxy = __shfl_sync(0xffffffffu, dm[0], q0 + 2);
             const float myy = __shfl_sync(0xffffffffu, dm[1], q0 + 2);
             if (fg < nrows && ft < 3) {
-                const float4 g0 = sm.ring_geo[warp][rp][0];
-                const float4 g1 = sm.ring_geo[warp][rp][1];
-                const uint32_t id = sm.ring_id[warp][rp];
+                const uint32_t id = sm.row_id[warp][fg];
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(geo + 8 * (size_t)id));       // L1/L2 hit: staged a moment ago
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(geo + 8 * (size_t)id + 4));
                 const float conx = g0.z, cony = g0.w, conz = g1.x, o = g1.y;
                 // sums over the pixels of q * (1, dx, dy, dx^2, dx dy, dy^2) with d = centre - pixel = c - x'
                 const float cx = g0.x - tcx, cy = g0.y - tcy;
@@ -320,9 +323,6 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
                 red_add(ggrad + (size_t)id * GG_STRIDE + sb, ub);
             }
         }
-        rseq += nrows;
-        rrow += nrows;
-        if (rrow >= BM_RING) rrow -= BM_RING;
         __syncwarp();   // every lane is done with the rows before they are overwritten
     };
 
@@ -340,30 +340,48 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
         const bool have_next_id = (b + 2 < nbatch) && tid < batch_cnt(b + 2);
         if (have_next_id) next_id = load_id(b + 2, tid);
 
-        // ---------------- phase A: thread = pixel ----------------
+        // ---------------- phase A ----------------
         if (pos_hi - (cnt - 1) < warp_n) {   // some pixel of this warp still has contributors in this batch
-            for (int j0 = 0; j0 < cnt; j0 += 4) {
-                if (pos_hi - (j0 + 3) >= warp_n) continue;                              // warp-uniform
-                float pw[4], op[4];
-                bool cd[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const float4 g0 = sm.geo[stage][j0 + i][0];
-                    const float4 g1 = sm.geo[stage][j0 + i][1];
-                    const float dx = g0.x - pixx, dy = g0.y - pixy;
-                    pw[i] = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
-                    cd[i] = (pos_hi - (j0 + i) < my_n) && !(pw[i] > 0.0f) && (pw[i] >= g1.z);
-                    op[i] = g1.y;
+#pragma unroll 1
+            for (int half = 0; half < BM_NB; half += 32) {
+                // block-level candidate test, lane = splat: can ANY point of the warp's 8x4 pixel block reach the
+                // splat's accept threshold?  power = -Q(d), Q convex: the minimum of Q over the block is 0 (centre
+                // inside) or sits on one of the four edges (clamped 1-D minimisation).  Conservative by a relative
+                // and an absolute margin; the per-pixel test below is the reference's and decides.
+                uint32_t cand;
+                {
+                    const int js = half + lane;
+                    const float4 g0 = sm.geo[stage][js][0];
+                    const float4 g1 = sm.geo[stage][js][1];
+                    const float ca = g0.z, cb = g0.w, cc = g1.x;
+                    const float dxl = g0.x - bx1, dxh = g0.x - bx0, dyl = g0.y - by1, dyh = g0.y - by0;   // d = centre - pixel
+                    float qmin = 0.f;
+                    if (!(dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f)) {
+                        const float ia = __frcp_rn(ca), ic = __frcp_rn(cc);
+                        auto q_at = [&](float dx, float dy) { return 0.5f * (ca * dx * dx + cc * dy * dy) + cb * dx * dy; };
+                        const float e0 = q_at(fminf(fmaxf(-cb * dyl * ia, dxl), dxh), dyl);
+                        const float e1 = q_at(fminf(fmaxf(-cb * dyh * ia, dxl), dxh), dyh);
+                        const float e2 = q_at(dxl, fminf(fmaxf(-cb * dxl * ic, dyl), dyh));
+                        const float e3 = q_at(dxh, fminf(fmaxf(-cb * dxh * ic, dyl), dyh));
+                        qmin = fminf(fminf(e0, e1), fminf(e2, e3));
+                    }
+                    const bool convex = ca > 0.f && cc > 0.f && ca * cc - cb * cb > 0.f;
+                    const bool reject = (convex && (qmin * (1.f - 1e-4f) - 1e-4f > -g1.z)) || !(g1.z < __int_as_float(0x7f800000));
+                    cand = __ballot_sync(0xffffffffu, !reject && (pos_hi - js < warp_n));
                 }
-                if (!__any_sync(0xffffffffu, cd[0] || cd[1] || cd[2] || cd[3])) continue;   // warp-uniform
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (!__any_sync(0xffffffffu, cd[i])) continue;                      // warp-uniform
-                    const int jj = j0 + i;
+                while (cand) {
+                    const int jj = half + __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    const float4 g0 = sm.geo[stage][jj][0];
+                    const float4 g1 = sm.geo[stage][jj][1];
+                    const float dx = g0.x - pixx, dy = g0.y - pixy;
+                    const float pw = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
+                    const bool cd = (pos_hi - jj < my_n) && !(pw > 0.0f) && (pw >= g1.z);
+                    if (!__any_sync(0xffffffffu, cd)) continue;                          // warp-uniform
                     float w = 0.f, q = 0.f;
-                    if (cd[i]) {
-                        const float G = expf(pw[i]);
-                        const float alpha = fminf(0.99f, op[i] * G);
+                    if (cd) {
+                        const float G = expf(pw);
+                        const float alpha = fminf(0.99f, g1.y * G);
                         if (!(alpha < 1.0f / 255.0f)) {
                             T = T / (1.f - alpha);
                             float s = 0.f;
@@ -390,15 +408,15 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
                         }
                     }
                     // append one row (all lanes write: zero where the pixel did not blend)
-                    const int col = (lane + 4 * (wseq & 7)) & 31;
-                    ringW[wrow * 32 + col] = w;
-                    ringQ[wrow * 32 + col] = q;
-                    if (lane < 2) sm.ring_geo[warp][wrow][lane] = sm.geo[stage][jj][lane];
-                    if (lane == 2) sm.ring_id[warp][wrow] = sm.ids[idb][jj];
-                    wseq++;
-                    wrow = (wrow == BM_RING - 1) ? 0 : wrow + 1;
+                    const int col = (lane + 4 * nrow) & 31;
+                    rowW[nrow * 32 + col] = w;
+                    rowQ[nrow * 32 + col] = q;
+                    if (lane == 0) sm.row_id[warp][nrow] = sm.ids[idb][jj];
+                    if (++nrow == BM_N) {
+                        flush_rows(BM_N);
+                        nrow = 0;
+                    }
                 }
-                if (wseq - rseq >= BM_N) flush_rows(BM_N);
             }
         }
 
@@ -408,7 +426,7 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
         if (b + 1 < nbatch) bm_pad_geo<NQ>(sm, stage ^ 1, batch_cnt(b + 1));
         __syncthreads();   // batch b+1 is visible; nobody reads the buffers of batch b any more
     }
-    if (wseq - rseq > 0) flush_rows(wseq - rseq);
+    if (nrow > 0) flush_rows(nrow);
 }
 
 template <int NQ, bool VEC, bool MD, bool COLOR>
