@@ -25,6 +25,7 @@
 // and three CTAs per SM.
 #include "common.cuh"
 #include "cp_async.cuh"
+#include "candidate.cuh"
 
 namespace sagars {
 
@@ -344,29 +345,14 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
         if (pos_hi - (cnt - 1) < warp_n) {   // some pixel of this warp still has contributors in this batch
 #pragma unroll 1
             for (int half = 0; half < BM_NB; half += 32) {
-                // block-level candidate test, lane = splat: can ANY point of the warp's 8x4 pixel block reach the
-                // splat's accept threshold?  power = -Q(d), Q convex: the minimum of Q over the block is 0 (centre
-                // inside) or sits on one of the four edges (clamped 1-D minimisation).  Conservative by a relative
-                // and an absolute margin; the per-pixel test below is the reference's and decides.
+                // block-level candidate test (candidate.cuh), lane = splat: can ANY point of the warp's 8x4 pixel
+                // block reach the splat's accept threshold?  The per-pixel test below is the reference's and decides.
                 uint32_t cand;
                 {
                     const int js = half + lane;
                     const float4 g0 = sm.geo[stage][js][0];
                     const float4 g1 = sm.geo[stage][js][1];
-                    const float ca = g0.z, cb = g0.w, cc = g1.x;
-                    const float dxl = g0.x - bx1, dxh = g0.x - bx0, dyl = g0.y - by1, dyh = g0.y - by0;   // d = centre - pixel
-                    float qmin = 0.f;
-                    if (!(dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f)) {
-                        const float ia = __frcp_rn(ca), ic = __frcp_rn(cc);
-                        auto q_at = [&](float dx, float dy) { return 0.5f * (ca * dx * dx + cc * dy * dy) + cb * dx * dy; };
-                        const float e0 = q_at(fminf(fmaxf(-cb * dyl * ia, dxl), dxh), dyl);
-                        const float e1 = q_at(fminf(fmaxf(-cb * dyh * ia, dxl), dxh), dyh);
-                        const float e2 = q_at(dxl, fminf(fmaxf(-cb * dxl * ic, dyl), dyh));
-                        const float e3 = q_at(dxh, fminf(fmaxf(-cb * dxh * ic, dyl), dyh));
-                        qmin = fminf(fminf(e0, e1), fminf(e2, e3));
-                    }
-                    const bool convex = ca > 0.f && cc > 0.f && ca * cc - cb * cb > 0.f;
-                    const bool reject = (convex && (qmin * (1.f - 1e-4f) - 1e-4f > -g1.z)) || !(g1.z < __int_as_float(0x7f800000));
+                    const bool reject = block_rejects(g0, g1, bx0, bx1, by0, by1);
                     cand = __ballot_sync(0xffffffffu, !reject && (pos_hi - js < warp_n));
                 }
                 while (cand) {

@@ -7,12 +7,15 @@
 //
 //   * a CTA is one 16x16 tile = two independent 128-pixel groups (4 warps each).  Thread t of a group owns pixel row t
 //     of that group's A operand and TMEM lane t of its accumulator D[128 x 32] (fp32, 32 TMEM columns per group);
-//   * per sub-batch of 16 splats every thread runs the scalar loop and keeps w[16] in registers (0 where the pair
-//     is rejected / the pixel is saturated), then writes its row of the K-major tf32 operand tiles W_hi / W_lo
-//     (SWIZZLE_NONE canonical layout) while 128 threads transpose-split the 16 feature rows into F_hi / F_lo;
-//   * one elected thread per group issues  D += W_lo F_hi + W_hi F_lo + W_hi F_hi  (3xTF32: 6 tcgen05.mma.kind::tf32
-//     of 128x32x8, ~2^-21 relative error) and commits to the group's mbarrier; the next sub-batch's scalar loop
-//     overlaps the MMAs and only waits for them right before it overwrites the operand tiles;
+//   * per staged batch of 64 splats every warp first tests the splats, one per lane, against its own 8x4 pixel block
+//     (candidate.cuh); the four warps of a group OR their candidate masks, and only the group's candidates (about half
+//     of the tile's list) become k-slots of the GEMM.  Taken four slots at a time in list order: a warp runs the
+//     reference's per-pixel test only for its own candidates (w = alpha * T, 0 otherwise), every thread writes its row
+//     of the K-major tf32 operand tiles W_hi / W_lo (SWIZZLE_NONE canonical layout) with one 16-byte store each, and
+//     the group's 128 threads transpose-split the four feature rows into F_hi / F_lo;
+//   * every 16 slots one elected thread per group issues  D += W_lo F_hi + W_hi F_lo + W_hi F_hi  (3xTF32: 6
+//     tcgen05.mma.kind::tf32 of 128x32x8, ~2^-21 relative error) and commits to the group's mbarrier; the next slots'
+//     scalar work overlaps the MMAs and only waits for them right before it overwrites the operand tiles;
 //   * at the end each thread reads its 32 channel sums with one tcgen05.ld and adds T * bg.
 //
 // The colour image differs from the SIMT kernel / the reference by fp32-level rounding only (3xTF32 and a different
@@ -20,11 +23,12 @@
 #include "common.cuh"
 #include "cp_async.cuh"
 #include "tc.cuh"
+#include "candidate.cuh"
 
 namespace sagars {
 
 constexpr int TCF_BATCH = 64;   // instances staged per cp.async stage
-constexpr int TCF_SUB = 16;     // instances per MMA sub-batch (2 k-steps of 8)
+constexpr int TCF_SUB = 16;     // k-slots per MMA issue (2 k-steps of 8)
 constexpr int TCF_N = 32;       // channels
 
 struct FwdTcSmem {
@@ -33,6 +37,7 @@ struct FwdTcSmem {
     float4 geo[2][TCF_BATCH][2];        // x, y, cx, cy | cz, opacity, accept_threshold, -
     float4 feat[2][TCF_BATCH][TCF_N / 4];
     uint32_t ids[2][TCF_BATCH];
+    uint32_t cmask[2][2][4][2];         // [batch parity][group][warp of the group][low, high 32 splats]: candidate masks
     uint64_t mbar[2];
     uint32_t tmem_base;
 };
@@ -88,6 +93,8 @@ render_forward_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __res
     {
         float* f = reinterpret_cast<float*>(&sm.feat[0][0][0]);
         for (int c = tid; c < 2 * TCF_BATCH * TCF_N; c += TILE_PIX) f[c] = 0.f;
+        float* bt = &sm.B[0][0][0];   // slots of a partially filled last chunk keep whatever is here: must be finite
+        for (int c = tid; c < 2 * 2 * TCF_SUB * TCF_N; c += TILE_PIX) bt[c] = 0.f;
     }
     if (tid == 0) {
         tc::mbar_init(&sm.mbar[0], 1);
@@ -103,11 +110,49 @@ render_forward_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __res
     float T = 1.0f;
     uint32_t last_contributor = 0;
     bool done = !inside;
-    uint32_t n_issued = 0;               // MMA sub-batches committed by this group so far (group-uniform)
+    uint32_t n_issued = 0;               // MMA issues committed by this group so far (group-uniform)
+    int nslot = 0;                       // k-slots of the current operand tiles already written (group-uniform, multiple of 4)
 
     constexpr uint32_t A_SBO = 128, A_LBO = 128 * 16;     // bytes
     constexpr uint32_t B_SBO = 128, B_LBO = 128 * (TCF_N / 8);
     constexpr uint32_t IDESC = tc::idesc_tf32(128, TCF_N, 0, 0);
+
+    // the warp's 8x4 pixel block (pixel centres), for the block-level candidate test
+    const float bx0 = (float)(blockIdx.x * TILE_X + (warp & 1) * 8), bx1 = bx0 + 7.f;
+    const float by0 = (float)(blockIdx.y * TILE_Y + (warp >> 1) * 4), by1 = by0 + 3.f;
+
+    float* const Ah = &sm.A[grp][0][(gt >> 3) * 32 + (gt & 7) * 4];
+    float* const Al = &sm.A[grp][1][(gt >> 3) * 32 + (gt & 7) * 4];
+    // F^T tiles: lane handles slot (lane & 3) of a chunk and channel 8 * (warp of the group) + lane / 4 -> 32 consecutive floats per warp
+    const int b_slot = lane & 3, b_ch = 8 * (warp & 3) + (lane >> 2);
+    float* const Bh = &sm.B[grp][0][(b_ch >> 3) * 32 + (b_ch & 7) * 4 + b_slot];
+    float* const Bl = &sm.B[grp][1][(b_ch >> 3) * 32 + (b_ch & 7) * 4 + b_slot];
+
+    // 16 slots are complete (or padded): hand the operand tiles to the tensor core
+    auto issue_mma = [&]() {
+        tc::fence_smem_to_async_proxy();
+        tc::fence_before_sync();
+        tc::bar_sync_128(1 + grp);
+        if (gt == 0) {
+            tc::fence_after_sync();
+            const uint32_t a_hi = smem_u32(&sm.A[grp][0][0]), a_lo = smem_u32(&sm.A[grp][1][0]);
+            const uint32_t b_hi = smem_u32(&sm.B[grp][0][0]), b_lo = smem_u32(&sm.B[grp][1][0]);
+#pragma unroll
+            for (int term = 0; term < 3; term++) {            // lo*hi, hi*lo, hi*hi (small terms first)
+                const uint32_t a0 = (term == 0) ? a_lo : a_hi;
+                const uint32_t b0 = (term == 1) ? b_lo : b_hi;
+#pragma unroll
+                for (int ks = 0; ks < TCF_SUB / 8; ks++) {
+                    const uint64_t da = tc::smem_desc(a0 + ks * 2 * A_LBO, A_LBO, A_SBO);
+                    const uint64_t db = tc::smem_desc(b0 + ks * 2 * B_LBO, B_LBO, B_SBO);
+                    tc::mma_tf32(tmem_d, da, db, IDESC, (n_issued > 0 || term > 0 || ks > 0) ? 1u : 0u);
+                }
+            }
+            tc::commit(&sm.mbar[grp]);
+        }
+        n_issued++;
+        nslot = 0;
+    };
 
     if (nbatch > 0) {
         if (tid < min(TCF_BATCH, total)) sm.ids[0][tid] = point_list[range.x + tid];
@@ -122,7 +167,6 @@ render_forward_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __res
 
     for (int b = 0; b < nbatch; b++) {
         const int stage = b & 1;
-        const int cnt = min(TCF_BATCH, total - b * TCF_BATCH);
         if (__syncthreads_and(done)) break;
 
         if (b + 1 < nbatch) {
@@ -134,104 +178,91 @@ render_forward_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __res
         const bool have_next_id = (b + 2 < nbatch) && tid < min(TCF_BATCH, rem2);
         if (have_next_id) next_id = point_list[range.x + (b + 2) * TCF_BATCH + tid];
 
-        for (int sb = 0; sb < cnt; sb += TCF_SUB) {
-            // ---- scalar part: w[j] = alpha * T of this pixel for the 16 splats of the sub-batch (0 if rejected) ----
-            float w[TCF_SUB];
-            const float4* gp = &sm.geo[stage][sb][0];
-            // four splats at a time: their `power` tests are independent (ILP, one vote per four); only the accepted
-            // ones are then taken in order, because T and `done` chain through them.  Records beyond the tile's list
-            // are sentinels (accept_threshold = +inf), so no bounds checks are needed here.
+        // ---- candidates: lane = splat against this warp's pixel block; the group ORs its four masks ----
+        uint64_t own, gm;
+        {
+            uint32_t c[2] = {0u, 0u};
+            if (!__all_sync(0xffffffffu, done)) {
 #pragma unroll
-            for (int j0 = 0; j0 < TCF_SUB; j0 += 4) {
-                float pw[4], op[4];
-                bool cd[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const float4 g0 = gp[2 * (j0 + i)];
-                    const float4 g1 = gp[2 * (j0 + i) + 1];
-                    const float dx = g0.x - pixx, dy = g0.y - pixy;
-                    pw[i] = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
-                    cd[i] = !(pw[i] > 0.0f) && (pw[i] >= g1.z);
-                    op[i] = g1.y;
-                    w[j0 + i] = 0.f;
+                for (int h = 0; h < 2; h++) {
+                    const float4 g0 = sm.geo[stage][32 * h + lane][0];
+                    const float4 g1 = sm.geo[stage][32 * h + lane][1];
+                    c[h] = __ballot_sync(0xffffffffu, !block_rejects(g0, g1, bx0, bx1, by0, by1));
                 }
-                const bool anyc = (cd[0] || cd[1] || cd[2] || cd[3]) && !done;
-                if (__any_sync(0xffffffffu, anyc)) {
+            }
+            if (lane < 2) sm.cmask[stage][grp][warp & 3][lane] = c[lane];
+            tc::bar_sync_128(1 + grp);
+            uint32_t glo = 0u, ghi = 0u;
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        if (cd[i] && !done) {
-                            const float alpha = fminf(0.99f, op[i] * expf(pw[i]));
+            for (int w4 = 0; w4 < 4; w4++) { glo |= sm.cmask[stage][grp][w4][0]; ghi |= sm.cmask[stage][grp][w4][1]; }
+            own = ((uint64_t)c[1] << 32) | c[0];
+            gm = ((uint64_t)ghi << 32) | glo;
+        }
+
+        // ---- the group's candidates, four k-slots at a time, in list order ----
+        while (gm) {
+            float wq[4];
+            int jsel = 0;                       // the splat whose feature row this lane transposes (slot lane & 3)
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                wq[i] = 0.f;
+                if (gm) {                                                              // group-uniform
+                    const int jj = __ffsll((long long)gm) - 1;
+                    gm &= gm - 1;
+                    if (b_slot == i) jsel = jj;
+                    if ((own >> jj) & 1ull) {                                          // warp-uniform
+                        const float4 g0 = sm.geo[stage][jj][0];
+                        const float4 g1 = sm.geo[stage][jj][1];
+                        const float dx = g0.x - pixx, dy = g0.y - pixy;
+                        const float pw = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
+                        const bool cd = !done && !(pw > 0.0f) && (pw >= g1.z);
+                        if (cd) {
+                            const float alpha = fminf(0.99f, g1.y * expf(pw));
                             if (!(alpha < 1.0f / 255.0f)) {
                                 const float test_T = T * (1 - alpha);
                                 if (test_T < 0.0001f) {
                                     done = true;
                                 } else {
-                                    w[j0 + i] = alpha * T;
+                                    wq[i] = alpha * T;
                                     T = test_T;
-                                    last_contributor = (uint32_t)(b * TCF_BATCH + sb + j0 + i + 1);
+                                    last_contributor = (uint32_t)(b * TCF_BATCH + jj + 1);
                                 }
                             }
                         }
                     }
                 }
             }
-
-            // ---- operand tiles: wait until the previous sub-batch's MMAs have consumed them, then rewrite ----
-            if (n_issued > 0) tc::mbar_wait(&sm.mbar[grp], (n_issued - 1) & 1);
+            // operand tiles: wait until the previous issue's MMAs have consumed them before the first rewrite
+            if (nslot == 0 && n_issued > 0) tc::mbar_wait(&sm.mbar[grp], (n_issued - 1) & 1);
             {
-                float* Ah = &sm.A[grp][0][(gt >> 3) * 32 + (gt & 7) * 4];
-                float* Al = &sm.A[grp][1][(gt >> 3) * 32 + (gt & 7) * 4];
-#pragma unroll
-                for (int c = 0; c < TCF_SUB / 4; c++) {
-                    float4 h, l;
-                    h.x = tc::tf32_hi(w[4 * c + 0]); l.x = w[4 * c + 0] - h.x;
-                    h.y = tc::tf32_hi(w[4 * c + 1]); l.y = w[4 * c + 1] - h.y;
-                    h.z = tc::tf32_hi(w[4 * c + 2]); l.z = w[4 * c + 2] - h.z;
-                    h.w = tc::tf32_hi(w[4 * c + 3]); l.w = w[4 * c + 3] - h.w;
-                    *reinterpret_cast<float4*>(Ah + c * 512) = h;
-                    *reinterpret_cast<float4*>(Al + c * 512) = l;
-                }
-                // feature rows -> F^T tiles (rows = channels, k = splat): thread (j, chunk) handles 4 channels of splat j
-                const int j = gt >> 3, c4 = gt & 7;
-                const float4 raw = sm.feat[stage][sb + j][c4];   // rows beyond cnt hold stale finite data; their w is 0
-                const float r[4] = {raw.x, raw.y, raw.z, raw.w};
-                float* Bh = &sm.B[grp][0][(j >> 2) * 128 + (j & 3)];
-                float* Bl = &sm.B[grp][1][(j >> 2) * 128 + (j & 3)];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int n = 4 * c4 + i;
-                    const float h = tc::tf32_hi(r[i]);
-                    Bh[(n >> 3) * 32 + (n & 7) * 4] = h;
-                    Bl[(n >> 3) * 32 + (n & 7) * 4] = r[i] - h;
-                }
+                float4 h, l;
+                h.x = tc::tf32_hi(wq[0]); l.x = wq[0] - h.x;
+                h.y = tc::tf32_hi(wq[1]); l.y = wq[1] - h.y;
+                h.z = tc::tf32_hi(wq[2]); l.z = wq[2] - h.z;
+                h.w = tc::tf32_hi(wq[3]); l.w = wq[3] - h.w;
+                *reinterpret_cast<float4*>(Ah + (nslot >> 2) * 512) = h;
+                *reinterpret_cast<float4*>(Al + (nslot >> 2) * 512) = l;
+                // unused slots of the last chunk of a batch take any staged row: their weight is 0 and the row is finite
+                const float f = reinterpret_cast<const float*>(&sm.feat[stage][jsel][0])[b_ch];
+                const float fh = tc::tf32_hi(f);
+                Bh[(nslot >> 2) * 128] = fh;
+                Bl[(nslot >> 2) * 128] = f - fh;
             }
-            tc::fence_smem_to_async_proxy();
-            tc::fence_before_sync();
-            tc::bar_sync_128(1 + grp);
-            if (gt == 0) {
-                tc::fence_after_sync();
-                const uint32_t a_hi = smem_u32(&sm.A[grp][0][0]), a_lo = smem_u32(&sm.A[grp][1][0]);
-                const uint32_t b_hi = smem_u32(&sm.B[grp][0][0]), b_lo = smem_u32(&sm.B[grp][1][0]);
-#pragma unroll
-                for (int term = 0; term < 3; term++) {            // lo*hi, hi*lo, hi*hi (small terms first)
-                    const uint32_t a0 = (term == 0) ? a_lo : a_hi;
-                    const uint32_t b0 = (term == 1) ? b_lo : b_hi;
-#pragma unroll
-                    for (int ks = 0; ks < TCF_SUB / 8; ks++) {
-                        const uint64_t da = tc::smem_desc(a0 + ks * 2 * A_LBO, A_LBO, A_SBO);
-                        const uint64_t db = tc::smem_desc(b0 + ks * 2 * B_LBO, B_LBO, B_SBO);
-                        tc::mma_tf32(tmem_d, da, db, IDESC, (n_issued > 0 || term > 0 || ks > 0) ? 1u : 0u);
-                    }
-                }
-                tc::commit(&sm.mbar[grp]);
-            }
-            n_issued++;
+            nslot += 4;
+            if (nslot == TCF_SUB) issue_mma();
         }
 
         if (have_next_id) sm.ids[b & 1][tid] = next_id;
         cp_async_wait_all();
         if (b + 1 < nbatch) tcf_pad_batch(sm, stage ^ 1, min(TCF_BATCH, total - (b + 1) * TCF_BATCH));
         __syncthreads();
+    }
+    if (nslot > 0) {   // last, partially filled operand tiles: zero weights in the remaining slots
+        for (int c = nslot >> 2; c < TCF_SUB / 4; c++) {
+            *reinterpret_cast<float4*>(Ah + c * 512) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(Al + c * 512) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        issue_mma();
     }
 
     // ---- epilogue: accumulator row -> registers -> planar image ----
