@@ -45,6 +45,7 @@ struct BmSmem {
     float rowW[8][BM_N][32];                        // per warp: row r, pixel p at (p + 4 r) & 31
     float rowQ[8][BM_N][32];
     uint32_t row_id[8][BM_N];                       // Gaussian index of the row
+    uint8_t clist[8][BM_NB];                        // per warp: batch-local indices of its candidate splats, in list order
     float4 geo[2][BM_NB][2];                        // staged records: x, y, cx, cy | cz, opacity, accept_threshold, -
     float4 feat[2][BM_NB][NQ];                      // staged feature rows, zero padded
     uint32_t ids[3][BM_NB];
@@ -138,6 +139,7 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
 
     const uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];
     const int total = (int)(range.y - range.x);
+    if (total <= 0) return;   // empty tile: nothing to differentiate (before the gradient rows are fetched)
 
     const float T_final = inside ? final_Ts[pix_id] : 0.f;
     const int my_n = inside ? (int)n_contrib[pix_id] : 0;
@@ -205,7 +207,6 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
     float T = T_final;
     float acc_r = 0.f, last_alpha = 0.f, last_s = 0.f;
 
-    int nrow = 0;   // rows waiting in this warp's tiles (warp-uniform)
     float* const rowW = &sm.rowW[warp][0][0];
     float* const rowQ = &sm.rowQ[warp][0][0];
 
@@ -343,47 +344,95 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
 
         // ---------------- phase A ----------------
         if (pos_hi - (cnt - 1) < warp_n) {   // some pixel of this warp still has contributors in this batch
+            // block-level candidate test (candidate.cuh), lane = splat: can ANY point of the warp's 8x4 pixel block reach
+            // the splat's accept threshold?  Survivors are compacted, in list order, into the warp's candidate list.
+            int ncand;
+            {
+                const uint32_t lt = (1u << lane) - 1u;
+                const bool k0 = !block_rejects(sm.geo[stage][lane][0], sm.geo[stage][lane][1], bx0, bx1, by0, by1) &&
+                                (pos_hi - lane < warp_n);
+                const bool k1 = !block_rejects(sm.geo[stage][32 + lane][0], sm.geo[stage][32 + lane][1], bx0, bx1, by0, by1) &&
+                                (pos_hi - (32 + lane) < warp_n);
+                const uint32_t c0 = __ballot_sync(0xffffffffu, k0), c1 = __ballot_sync(0xffffffffu, k1);
+                const int n0 = __popc(c0);
+                if (k0) sm.clist[warp][__popc(c0 & lt)] = (uint8_t)lane;
+                if (k1) sm.clist[warp][n0 + __popc(c1 & lt)] = (uint8_t)(32 + lane);
+                ncand = n0 + __popc(c1);
+                __syncwarp();
+            }
 #pragma unroll 1
-            for (int half = 0; half < BM_NB; half += 32) {
-                // block-level candidate test (candidate.cuh), lane = splat: can ANY point of the warp's 8x4 pixel
-                // block reach the splat's accept threshold?  The per-pixel test below is the reference's and decides.
-                uint32_t cand;
-                {
-                    const int js = half + lane;
-                    const float4 g0 = sm.geo[stage][js][0];
-                    const float4 g1 = sm.geo[stage][js][1];
-                    const bool reject = block_rejects(g0, g1, bx0, bx1, by0, by1);
-                    cand = __ballot_sync(0xffffffffu, !reject && (pos_hi - js < warp_n));
+            for (int k0 = 0; k0 < ncand; k0 += BM_N) {
+                const int m = min(BM_N, ncand - k0);   // candidates of this group = rows of the operand tiles
+                // ---- (1) s[p][i] = f_i . g_p for the group's candidates as a tensor-core product (3xTF32):
+                //          S (32 pixels x 8) = G (32 x C) * F^T (C x 8).  The feature rows are first gathered into the W
+                //          tile's storage (row i, channel c at (c + 4 i) & 31), S lands in the Q tile's storage with the
+                //          Q layout, so the lane that later writes Q[i][p] is the one that reads S[i][p].
+                if (COLOR) {
+                    float sacc[2][4];
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) sacc[mt][0] = sacc[mt][1] = sacc[mt][2] = sacc[mt][3] = 0.f;
+                    constexpr int QR = (ROW < 32 ? ROW : 32) / 4;      // feature quads per row and channel block
+#pragma unroll 1
+                    for (int cb = 0; cb < ROW; cb += 32) {
+                        if (cb > 0) __syncwarp();
+                        for (int idx = lane; idx < BM_N * QR; idx += 32) {
+                            const int r = idx / QR, qd = idx - r * QR;
+                            const int jr = sm.clist[warp][min(k0 + r, ncand - 1)];
+                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if ((cb >> 2) + qd < NQ) v = sm.feat[stage][jr][(cb >> 2) + qd];
+                            *reinterpret_cast<float4*>(rowW + r * 32 + 4 * ((qd + r) & 7)) = v;
+                        }
+                        __syncwarp();
+                        const float* Fr = rowW + fg * 32;
+#pragma unroll 1
+                        for (int ks = 0; ks < QR / 2; ks++) {
+                            uint32_t bh0, bl0, bh1, bl1;
+                            split_tf32(Fr[(ks * 8 + ft + 4 * fg) & 31], bh0, bl0);
+                            split_tf32(Fr[(ks * 8 + ft + 4 + 4 * fg) & 31], bh1, bl1);
+                            const int ch0 = cb + ks * 8 + ft, ch1 = ch0 + 4;
+#pragma unroll
+                            for (int mt = 0; mt < 2; mt++) {
+                                // pixels 16 mt + fg and + 8 of the warp's block: raster rows 2 mt and 2 mt + 1, x = fg
+                                const int p0 = ((warp >> 1) * 4 + 2 * mt) * TILE_X + (warp & 1) * 8 + fg, p1 = p0 + TILE_X;
+                                uint32_t ah[4], al[4];
+                                split_tf32(sm.Gs[p0][4 * (((ch0 >> 2) + p0) & (NQE - 1)) + (ch0 & 3)], ah[0], al[0]);
+                                split_tf32(sm.Gs[p1][4 * (((ch0 >> 2) + p1) & (NQE - 1)) + (ch0 & 3)], ah[1], al[1]);
+                                split_tf32(sm.Gs[p0][4 * (((ch1 >> 2) + p0) & (NQE - 1)) + (ch1 & 3)], ah[2], al[2]);
+                                split_tf32(sm.Gs[p1][4 * (((ch1 >> 2) + p1) & (NQE - 1)) + (ch1 & 3)], ah[3], al[3]);
+                                mma_16n8k8(sacc[mt], al[0], al[1], al[2], al[3], bh0, bh1);
+                                mma_16n8k8(sacc[mt], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+                                mma_16n8k8(sacc[mt], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+                            }
+                        }
+                    }
+                    // fragment (pixel 16 mt + fg [+8], candidates 2 ft, 2 ft + 1) -> S[i][(p + 4 i) & 31]
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) {
+                        const int pa = 16 * mt + fg, pb = pa + 8;
+                        rowQ[(2 * ft) * 32 + ((pa + 8 * ft) & 31)] = sacc[mt][0];
+                        rowQ[(2 * ft + 1) * 32 + ((pa + 8 * ft + 4) & 31)] = sacc[mt][1];
+                        rowQ[(2 * ft) * 32 + ((pb + 8 * ft) & 31)] = sacc[mt][2];
+                        rowQ[(2 * ft + 1) * 32 + ((pb + 8 * ft + 4) & 31)] = sacc[mt][3];
+                    }
+                    __syncwarp();
                 }
-                while (cand) {
-                    const int jj = half + __ffs(cand) - 1;
-                    cand &= cand - 1;
+                // ---- (2) thread = pixel over the group's candidates (the reference's traversal): row i of W / Q ----
+#pragma unroll 1
+                for (int i = 0; i < m; i++) {
+                    const int jj = sm.clist[warp][k0 + i];
                     const float4 g0 = sm.geo[stage][jj][0];
                     const float4 g1 = sm.geo[stage][jj][1];
                     const float dx = g0.x - pixx, dy = g0.y - pixy;
                     const float pw = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
                     const bool cd = (pos_hi - jj < my_n) && !(pw > 0.0f) && (pw >= g1.z);
-                    if (!__any_sync(0xffffffffu, cd)) continue;                          // warp-uniform
+                    const int col = (lane + 4 * i) & 31;
                     float w = 0.f, q = 0.f;
                     if (cd) {
                         const float G = expf(pw);
                         const float alpha = fminf(0.99f, g1.y * G);
                         if (!(alpha < 1.0f / 255.0f)) {
                             T = T / (1.f - alpha);
-                            float s = 0.f;
-                            if (COLOR) {
-                                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-                                for (int qd = 0; qd < NQ; qd++) {
-                                    const float4 f = sm.feat[stage][jj][qd];
-                                    const float4 gv = *reinterpret_cast<const float4*>(&sm.Gs[rl][4 * ((qd + rl) & (NQE - 1))]);
-                                    s0 += f.x * gv.x;
-                                    s1 += f.y * gv.y;
-                                    s2 += f.z * gv.z;
-                                    s3 += f.w * gv.w;
-                                }
-                                s = (s0 + s1) + (s2 + s3);
-                            }
+                            const float s = COLOR ? rowQ[i * 32 + col] : 0.f;
                             acc_r = last_alpha * last_s + (1.f - last_alpha) * acc_r;
                             last_s = s;
                             float dL_dalpha = (s - acc_r) * T;
@@ -393,16 +442,12 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
                             q = G * dL_dalpha;
                         }
                     }
-                    // append one row (all lanes write: zero where the pixel did not blend)
-                    const int col = (lane + 4 * nrow) & 31;
-                    rowW[nrow * 32 + col] = w;
-                    rowQ[nrow * 32 + col] = q;
-                    if (lane == 0) sm.row_id[warp][nrow] = sm.ids[idb][jj];
-                    if (++nrow == BM_N) {
-                        flush_rows(BM_N);
-                        nrow = 0;
-                    }
+                    rowW[i * 32 + col] = w;   // all lanes write: zero where the pixel did not blend
+                    rowQ[i * 32 + col] = q;
+                    if (lane == 0) sm.row_id[warp][i] = sm.ids[idb][jj];
                 }
+                // ---- (3) the rows' products leave for global memory ----
+                flush_rows(m);
             }
         }
 
@@ -412,7 +457,6 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
         if (b + 1 < nbatch) bm_pad_geo<NQ>(sm, stage ^ 1, batch_cnt(b + 1));
         __syncthreads();   // batch b+1 is visible; nobody reads the buffers of batch b any more
     }
-    if (nrow > 0) flush_rows(nrow);
 }
 
 template <int NQ, bool VEC, bool MD, bool COLOR>

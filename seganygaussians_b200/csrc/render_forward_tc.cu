@@ -179,77 +179,76 @@ render_forward_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __res
         if (have_next_id) next_id = point_list[range.x + (b + 2) * TCF_BATCH + tid];
 
         // ---- candidates: lane = splat against this warp's pixel block; the group ORs its four masks ----
-        uint64_t own, gm;
+        uint32_t own_lo = 0u, own_hi = 0u, grp_lo = 0u, grp_hi = 0u;
         {
-            uint32_t c[2] = {0u, 0u};
             if (!__all_sync(0xffffffffu, done)) {
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const float4 g0 = sm.geo[stage][32 * h + lane][0];
-                    const float4 g1 = sm.geo[stage][32 * h + lane][1];
-                    c[h] = __ballot_sync(0xffffffffu, !block_rejects(g0, g1, bx0, bx1, by0, by1));
-                }
+                own_lo = __ballot_sync(0xffffffffu, !block_rejects(sm.geo[stage][lane][0], sm.geo[stage][lane][1], bx0, bx1, by0, by1));
+                own_hi = __ballot_sync(0xffffffffu, !block_rejects(sm.geo[stage][32 + lane][0], sm.geo[stage][32 + lane][1], bx0, bx1, by0, by1));
             }
-            if (lane < 2) sm.cmask[stage][grp][warp & 3][lane] = c[lane];
+            if (lane == 0) { sm.cmask[stage][grp][warp & 3][0] = own_lo; sm.cmask[stage][grp][warp & 3][1] = own_hi; }
             tc::bar_sync_128(1 + grp);
-            uint32_t glo = 0u, ghi = 0u;
 #pragma unroll
-            for (int w4 = 0; w4 < 4; w4++) { glo |= sm.cmask[stage][grp][w4][0]; ghi |= sm.cmask[stage][grp][w4][1]; }
-            own = ((uint64_t)c[1] << 32) | c[0];
-            gm = ((uint64_t)ghi << 32) | glo;
+            for (int w4 = 0; w4 < 4; w4++) { grp_lo |= sm.cmask[stage][grp][w4][0]; grp_hi |= sm.cmask[stage][grp][w4][1]; }
         }
 
-        // ---- the group's candidates, four k-slots at a time, in list order ----
-        while (gm) {
-            float wq[4];
-            int jsel = 0;                       // the splat whose feature row this lane transposes (slot lane & 3)
+        // ---- the group's candidates, four k-slots at a time, in list order (32-bit masks: one half of the batch at a time) ----
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+            uint32_t gm = half ? grp_hi : grp_lo;
+            const uint32_t own = half ? own_hi : own_lo;
+            const float4* gp = &sm.geo[stage][32 * half][0];
+            const float* fp = reinterpret_cast<const float*>(&sm.feat[stage][32 * half][0]) + b_ch;
+            while (gm) {
+                float wq[4];
+                int jsel = 0;                   // the splat whose feature row this lane transposes (slot lane & 3)
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                wq[i] = 0.f;
-                if (gm) {                                                              // group-uniform
-                    const int jj = __ffsll((long long)gm) - 1;
-                    gm &= gm - 1;
-                    if (b_slot == i) jsel = jj;
-                    if ((own >> jj) & 1ull) {                                          // warp-uniform
-                        const float4 g0 = sm.geo[stage][jj][0];
-                        const float4 g1 = sm.geo[stage][jj][1];
-                        const float dx = g0.x - pixx, dy = g0.y - pixy;
-                        const float pw = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
-                        const bool cd = !done && !(pw > 0.0f) && (pw >= g1.z);
-                        if (cd) {
-                            const float alpha = fminf(0.99f, g1.y * expf(pw));
-                            if (!(alpha < 1.0f / 255.0f)) {
-                                const float test_T = T * (1 - alpha);
-                                if (test_T < 0.0001f) {
-                                    done = true;
-                                } else {
-                                    wq[i] = alpha * T;
-                                    T = test_T;
-                                    last_contributor = (uint32_t)(b * TCF_BATCH + jj + 1);
+                for (int i = 0; i < 4; i++) {
+                    wq[i] = 0.f;
+                    if (gm) {                                                          // group-uniform
+                        const int jj = __ffs(gm) - 1;
+                        gm &= gm - 1;
+                        if (b_slot == i) jsel = jj;
+                        if ((own >> jj) & 1u) {                                        // warp-uniform
+                            const float4 g0 = gp[2 * jj];
+                            const float4 g1 = gp[2 * jj + 1];
+                            const float dx = g0.x - pixx, dy = g0.y - pixy;
+                            const float pw = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
+                            const bool cd = !done && !(pw > 0.0f) && (pw >= g1.z);
+                            if (cd) {
+                                const float alpha = fminf(0.99f, g1.y * expf(pw));
+                                if (!(alpha < 1.0f / 255.0f)) {
+                                    const float test_T = T * (1 - alpha);
+                                    if (test_T < 0.0001f) {
+                                        done = true;
+                                    } else {
+                                        wq[i] = alpha * T;
+                                        T = test_T;
+                                        last_contributor = (uint32_t)(b * TCF_BATCH + 32 * half + jj + 1);
+                                    }
                                 }
                             }
                         }
                     }
                 }
+                // operand tiles: wait until the previous issue's MMAs have consumed them before the first rewrite
+                if (nslot == 0 && n_issued > 0) tc::mbar_wait(&sm.mbar[grp], (n_issued - 1) & 1);
+                {
+                    float4 h, l;
+                    h.x = tc::tf32_hi(wq[0]); l.x = wq[0] - h.x;
+                    h.y = tc::tf32_hi(wq[1]); l.y = wq[1] - h.y;
+                    h.z = tc::tf32_hi(wq[2]); l.z = wq[2] - h.z;
+                    h.w = tc::tf32_hi(wq[3]); l.w = wq[3] - h.w;
+                    *reinterpret_cast<float4*>(Ah + (nslot >> 2) * 512) = h;
+                    *reinterpret_cast<float4*>(Al + (nslot >> 2) * 512) = l;
+                    // unused slots of a half's last chunk take any staged row: their weight is 0 and the row is finite
+                    const float f = fp[jsel * TCF_N];
+                    const float fh = tc::tf32_hi(f);
+                    Bh[(nslot >> 2) * 128] = fh;
+                    Bl[(nslot >> 2) * 128] = f - fh;
+                }
+                nslot += 4;
+                if (nslot == TCF_SUB) issue_mma();
             }
-            // operand tiles: wait until the previous issue's MMAs have consumed them before the first rewrite
-            if (nslot == 0 && n_issued > 0) tc::mbar_wait(&sm.mbar[grp], (n_issued - 1) & 1);
-            {
-                float4 h, l;
-                h.x = tc::tf32_hi(wq[0]); l.x = wq[0] - h.x;
-                h.y = tc::tf32_hi(wq[1]); l.y = wq[1] - h.y;
-                h.z = tc::tf32_hi(wq[2]); l.z = wq[2] - h.z;
-                h.w = tc::tf32_hi(wq[3]); l.w = wq[3] - h.w;
-                *reinterpret_cast<float4*>(Ah + (nslot >> 2) * 512) = h;
-                *reinterpret_cast<float4*>(Al + (nslot >> 2) * 512) = l;
-                // unused slots of the last chunk of a batch take any staged row: their weight is 0 and the row is finite
-                const float f = reinterpret_cast<const float*>(&sm.feat[stage][jsel][0])[b_ch];
-                const float fh = tc::tf32_hi(f);
-                Bh[(nslot >> 2) * 128] = fh;
-                Bl[(nslot >> 2) * 128] = f - fh;
-            }
-            nslot += 4;
-            if (nslot == TCF_SUB) issue_mma();
         }
 
         if (have_next_id) sm.ids[b & 1][tid] = next_id;
