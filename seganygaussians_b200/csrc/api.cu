@@ -366,7 +366,7 @@ int sagars_forward(const sagars_forward_args* a,
     if (tr) {
         t5 = now_us();
         fprintf(stderr, "[sagars trace] fwd host us: alloc(geom,img)=%.0f launch(pre,scan)=%.0f wait-before=%.0f rest(+wait)=%.0f "
-                        "total=%.0f\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t0);
+                        "total=%.0f returned-at=%.0f\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t0, t5);
     }
     return SAGARS_OK;
 }
@@ -410,8 +410,11 @@ int sagars_backward(const sagars_backward_args* a, void* stream_)
     if (a->R > 0) point_list = binning_view(const_cast<void*>(a->binning_buffer), (size_t)a->R).point_list;
     float* ggrad = (float*)a->grad_scratch;
 
+    const bool tr = trace_on();
+    const double t0 = tr ? now_us() : 0;
     SAGARS_CUDA(cudaMemsetAsync(ggrad, 0, (size_t)d.P * GG_STRIDE * sizeof(float), s));
     if (!mask_only) SAGARS_CUDA(cudaMemsetAsync(a->dL_dcolors, 0, (size_t)d.P * d.C * sizeof(float), s));
+    const double t1 = tr ? now_us() : 0;
     if (a->R > 0) {
         {
             ProfScope ps(ST_RENDER_BWD, s);
@@ -420,6 +423,7 @@ int sagars_backward(const sagars_backward_args* a, void* stream_)
         }
         if (rc) return rc;
     }
+    if (tr) fprintf(stderr, "[sagars trace] bwd host us: memsets=%.0f launch(render_backward)=%.0f at=%.0f\n", t1 - t0, now_us() - t1, t0);
     if (mask_only) {
         // mask-only path: the only gradient is dL_dmask (DEPTH __init__.py:280-289)
         SAGARS_CUDA(cudaMemcpy2DAsync(a->dL_dmask, sizeof(float), ggrad + 6, GG_STRIDE * sizeof(float), sizeof(float),

@@ -383,7 +383,15 @@ static int launch_bwd_t(const sagars_backward_args& a, const Dims& d, GeomView g
 {
     auto kern = render_backward_kernel<NQ, VEC, MD, COLOR>;
     const size_t smem = sizeof(BwdSmem<NQ>);
-    SAGARS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {   // opt in to the dynamic shared-memory size once per device (not on every launch: the call takes the context lock)
+        static uint64_t done_mask = 0;
+        int dev = 0;
+        SAGARS_CUDA(cudaGetDevice(&dev));
+        if (!((done_mask >> (dev & 63)) & 1ull)) {
+            SAGARS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            done_mask |= 1ull << (dev & 63);
+        }
+    }
     dim3 grid(d.tiles_x, d.tiles_y);
     kern<<<grid, TILE_PIX, smem, s>>>(im.ranges, point_list, d.W, d.H, d.C, a.background, g.geo, features,
                                       im.final_T, im.n_contrib, a.dL_dout_color, a.dL_dout_mask, ggrad,

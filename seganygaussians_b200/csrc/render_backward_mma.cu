@@ -49,7 +49,7 @@ struct BmSmem {
     float4 geo[2][BM_NB][2];                        // staged records: x, y, cx, cy | cz, opacity, accept_threshold, -
     float4 feat[2][BM_NB][NQ];                      // staged feature rows, zero padded
     uint32_t ids[3][BM_NB];
-    uint32_t max_contrib;
+    uint32_t warp_max[8];                           // deepest contributing list position per warp
 };
 
 __device__ __forceinline__ uint32_t f2tf32(float x)
@@ -145,7 +145,25 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
     const int my_n = inside ? (int)n_contrib[pix_id] : 0;
 
     // ---- one-time setup -------------------------------------------------------------------------------------------
-    if (tid == 0) sm.max_contrib = 0;
+    // Two independent latency chains start here and overlap: (a) the upstream gradient row of this pixel (C strided
+    // loads from the planar image, held in registers until (b) is under way), (b) n_contrib -> deepest list position
+    // of the tile -> Gaussian ids of the first batch -> their records / feature rows.
+    float gr[ROW];
+    {
+        float gmask = 0.f;
+        if (MD) gmask = inside ? dL_dout_mask[pix_id] : 0.f;
+#pragma unroll
+        for (int k = 0; k < ROW; k++) {
+            float x = 0.f;
+            if (COLOR && k < K) x = inside ? dL_dpix[(size_t)k * plane + pix_id] : 0.f;
+            if (MD && k == K) x = gmask;   // the mask gradient rides as channel K of the colour product
+            gr[k] = x;
+        }
+    }
+    int warp_n = my_n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) warp_n = max(warp_n, __shfl_xor_sync(0xffffffffu, warp_n, o));
+    if (lane == 0) sm.warp_max[warp] = (uint32_t)warp_n;
     {   // rows past the fill level are multiplied too (their products are never used): start from finite values
         float* w = &sm.rowW[warp][0][0];
         float* q = &sm.rowQ[warp][0][0];
@@ -158,48 +176,32 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
         for (int c = tid; c < 2 * BM_NB * 4 * NQ; c += TILE_PIX) f[c] = 0.f;
     }
     __syncthreads();
-    int warp_n = my_n;
+    int maxc = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) warp_n = max(warp_n, __shfl_xor_sync(0xffffffffu, warp_n, o));
-    if (lane == 0 && warp_n > 0) atomicMax(&sm.max_contrib, (uint32_t)warp_n);
-
-    // upstream gradient row of this pixel -> swizzled smem row (quad q at physical quad (q + rl) % NQE)
-    float bgdot = 0.f;
-    {
-        float gmask = 0.f;
-        if (MD) gmask = inside ? dL_dout_mask[pix_id] : 0.f;
-#pragma unroll
-        for (int q = 0; q < NQE; q++) {
-            float v[4];
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const int k = 4 * q + c;
-                float x = 0.f;
-                if (COLOR && k < K) {
-                    x = inside ? dL_dpix[(size_t)k * plane + pix_id] : 0.f;
-                    bgdot += bg[k] * x;
-                }
-                if (MD && k == K) x = gmask;   // the mask gradient rides as channel K of the colour product
-                v[c] = x;
-            }
-            *reinterpret_cast<float4*>(&sm.Gs[rl][4 * ((q + rl) & (NQE - 1))]) = make_float4(v[0], v[1], v[2], v[3]);
-        }
-    }
-    __syncthreads();
-
-    const int maxc = min((int)sm.max_contrib, total);
+    for (int w8 = 0; w8 < 8; w8++) maxc = max(maxc, (int)sm.warp_max[w8]);
+    maxc = min(maxc, total);
     if (maxc <= 0) return;
     const int nbatch = (maxc + BM_NB - 1) / BM_NB;
     // batch b covers list positions pos_hi(b) - jj, jj = 0 .. cnt(b)-1, with pos_hi(b) = maxc - 1 - b*NB
     auto batch_cnt = [&](int b) { return min(BM_NB, maxc - b * BM_NB); };
     auto load_id = [&](int b, int jj) { return point_list[range.x + (maxc - 1 - b * BM_NB - jj)]; };
 
-    // prologue: ids(0), ids(1); records + features of batch 0
+    // ids(0), ids(1); records + features of batch 0
     if (tid < batch_cnt(0)) sm.ids[0][tid] = load_id(0, tid);
     __syncthreads();
     bm_issue_batch<NQ>(sm, 0, 0, batch_cnt(0), K, VEC, COLOR, geo, features);
     cp_async_commit();
     if (nbatch > 1 && tid < batch_cnt(1)) sm.ids[1][tid] = load_id(1, tid);
+
+    // the gradient row -> swizzled smem row (quad q at physical quad (q + rl) % NQE)
+    float bgdot = 0.f;
+#pragma unroll
+    for (int q = 0; q < NQE; q++) {
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            if (COLOR && 4 * q + c < K) bgdot += bg[4 * q + c] * gr[4 * q + c];
+        *reinterpret_cast<float4*>(&sm.Gs[rl][4 * ((q + rl) & (NQE - 1))]) = make_float4(gr[4 * q], gr[4 * q + 1], gr[4 * q + 2], gr[4 * q + 3]);
+    }
     cp_async_wait_all();
     bm_pad_geo<NQ>(sm, 0, batch_cnt(0));
     __syncthreads();
@@ -236,7 +238,7 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
         const float xb0 = (fg == 2) ? 1.f : (fg == 4) ? x0 : 0.f;
         const float xb1 = (fg == 2) ? 1.f : (fg == 4) ? x1 : 0.f;
         const float xc = (fg == 5) ? 1.f : 0.f;
-#pragma unroll 1
+#pragma unroll
         for (int ks = 0; ks < 4; ks++) {
             const int c0 = (ks * 8 + ft + 4 * fg) & 31, c1 = (c0 + 4) & 31;
             uint32_t wh0, wl0, wh1, wl1, qh0, ql0, qh1, ql1;
@@ -384,7 +386,7 @@ render_backward_mma_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
                         }
                         __syncwarp();
                         const float* Fr = rowW + fg * 32;
-#pragma unroll 1
+#pragma unroll
                         for (int ks = 0; ks < QR / 2; ks++) {
                             uint32_t bh0, bl0, bh1, bl1;
                             split_tf32(Fr[(ks * 8 + ft + 4 * fg) & 31], bh0, bl0);
@@ -465,7 +467,15 @@ static int launch_bwd_mma_t(const sagars_backward_args& a, const Dims& d, GeomVi
 {
     auto kern = render_backward_mma_kernel<NQ, VEC, MD, COLOR>;
     const size_t smem = sizeof(BmSmem<NQ>);
-    SAGARS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {   // opt in to the dynamic shared-memory size once per device (not on every launch: the call takes the context lock)
+        static uint64_t done_mask = 0;
+        int dev = 0;
+        SAGARS_CUDA(cudaGetDevice(&dev));
+        if (!((done_mask >> (dev & 63)) & 1ull)) {
+            SAGARS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            done_mask |= 1ull << (dev & 63);
+        }
+    }
     dim3 grid(d.tiles_x, d.tiles_y);
     kern<<<grid, TILE_PIX, smem, s>>>(im.ranges, point_list, d.W, d.H, d.C, a.background, g.geo, features,
                                       im.final_T, im.n_contrib, a.dL_dout_color, a.dL_dout_mask, ggrad,

@@ -233,7 +233,15 @@ static int launch_fwd_t(const sagars_forward_args& a, const Dims& d, GeomView g,
 {
     auto kern = render_forward_kernel<NQ, VEC, MD, COLOR>;
     const size_t smem = sizeof(FwdSmem<NQ>);
-    SAGARS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {   // opt in to the dynamic shared-memory size once per device (not on every launch: the call takes the context lock)
+        static uint64_t done_mask = 0;
+        int dev = 0;
+        SAGARS_CUDA(cudaGetDevice(&dev));
+        if (!((done_mask >> (dev & 63)) & 1ull)) {
+            SAGARS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            done_mask |= 1ull << (dev & 63);
+        }
+    }
     dim3 grid(d.tiles_x, d.tiles_y);
     kern<<<grid, TILE_PIX, smem, s>>>(im.ranges, point_list, d.W, d.H, d.C, g.geo, features, a.mask, g.depths, a.background,
                                       im.final_T, im.n_contrib, a.out_color, a.out_mask, a.out_depth);

@@ -291,7 +291,15 @@ int launch_render_forward_tc(const sagars_forward_args& a, const Dims& d, GeomVi
 {
     auto kern = render_forward_tc_kernel;
     const size_t smem = sizeof(FwdTcSmem) + 1024;
-    SAGARS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {   // opt in to the dynamic shared-memory size once per device (not on every launch: the call takes the context lock)
+        static uint64_t done_mask = 0;
+        int dev = 0;
+        SAGARS_CUDA(cudaGetDevice(&dev));
+        if (!((done_mask >> (dev & 63)) & 1ull)) {
+            SAGARS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            done_mask |= 1ull << (dev & 63);
+        }
+    }
     dim3 grid(d.tiles_x, d.tiles_y);
     kern<<<grid, TILE_PIX, smem, s>>>(im.ranges, point_list, d.W, d.H, g.geo, a.colors_precomp, a.background,
                                       im.final_T, im.n_contrib, a.out_color);
