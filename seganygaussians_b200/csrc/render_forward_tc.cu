@@ -38,6 +38,7 @@ struct FwdTcSmem {
     float4 feat[2][TCF_BATCH][TCF_N / 4];
     uint32_t ids[2][TCF_BATCH];
     uint32_t cmask[2][2][4][2];         // [batch parity][group][warp of the group][low, high 32 splats]: candidate masks
+    uint8_t glist[8][TCF_BATCH + 4];    // per warp: its copy of the group's candidate list (+ padding of the last chunk)
     uint64_t mbar[2];
     uint32_t tmem_base;
 };
@@ -179,8 +180,11 @@ render_forward_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __res
         if (have_next_id) next_id = point_list[range.x + (b + 2) * TCF_BATCH + tid];
 
         // ---- candidates: lane = splat against this warp's pixel block; the group ORs its four masks ----
-        uint32_t own_lo = 0u, own_hi = 0u, grp_lo = 0u, grp_hi = 0u;
+        // Every warp then writes its own copy of the group's candidate list (in list order): entry = batch-local splat
+        // index | 0x80 when the splat is also a candidate of THIS warp's block.  Four entries = one 32-bit word.
+        int ng;
         {
+            uint32_t own_lo = 0u, own_hi = 0u, grp_lo = 0u, grp_hi = 0u;
             if (!__all_sync(0xffffffffu, done)) {
                 own_lo = __ballot_sync(0xffffffffu, !block_rejects(sm.geo[stage][lane][0], sm.geo[stage][lane][1], bx0, bx1, by0, by1));
                 own_hi = __ballot_sync(0xffffffffu, !block_rejects(sm.geo[stage][32 + lane][0], sm.geo[stage][32 + lane][1], bx0, bx1, by0, by1));
@@ -189,66 +193,68 @@ render_forward_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __res
             tc::bar_sync_128(1 + grp);
 #pragma unroll
             for (int w4 = 0; w4 < 4; w4++) { grp_lo |= sm.cmask[stage][grp][w4][0]; grp_hi |= sm.cmask[stage][grp][w4][1]; }
+            const uint32_t lt = (1u << lane) - 1u;
+            const int n_lo = __popc(grp_lo);
+            ng = n_lo + __popc(grp_hi);
+            uint8_t* gl = &sm.glist[warp][0];
+            if ((grp_lo >> lane) & 1u) gl[__popc(grp_lo & lt)] = (uint8_t)(lane | (((own_lo >> lane) & 1u) << 7));
+            if ((grp_hi >> lane) & 1u) gl[n_lo + __popc(grp_hi & lt)] = (uint8_t)((32 + lane) | (((own_hi >> lane) & 1u) << 7));
+            if (lane < 3) gl[ng + lane] = 0;   // padding of the last chunk: staged row 0, not a candidate -> weight 0
+            __syncwarp();
         }
 
-        // ---- the group's candidates, four k-slots at a time, in list order (32-bit masks: one half of the batch at a time) ----
+        // ---- the group's candidates, four k-slots at a time, in list order ----
+        const float4* gp = &sm.geo[stage][0][0];
+        const float* fp = reinterpret_cast<const float*>(&sm.feat[stage][0][0]) + b_ch;
 #pragma unroll 1
-        for (int half = 0; half < 2; half++) {
-            uint32_t gm = half ? grp_hi : grp_lo;
-            const uint32_t own = half ? own_hi : own_lo;
-            const float4* gp = &sm.geo[stage][32 * half][0];
-            const float* fp = reinterpret_cast<const float*>(&sm.feat[stage][32 * half][0]) + b_ch;
-            while (gm) {
-                float wq[4];
-                int jsel = 0;                   // the splat whose feature row this lane transposes (slot lane & 3)
+        for (int k0 = 0; k0 < ng; k0 += 4) {
+            const uint32_t ent = *reinterpret_cast<const uint32_t*>(&sm.glist[warp][k0]);   // 4 entries
+            float wq[4];
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    wq[i] = 0.f;
-                    if (gm) {                                                          // group-uniform
-                        const int jj = __ffs(gm) - 1;
-                        gm &= gm - 1;
-                        if (b_slot == i) jsel = jj;
-                        if ((own >> jj) & 1u) {                                        // warp-uniform
-                            const float4 g0 = gp[2 * jj];
-                            const float4 g1 = gp[2 * jj + 1];
-                            const float dx = g0.x - pixx, dy = g0.y - pixy;
-                            const float pw = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
-                            const bool cd = !done && !(pw > 0.0f) && (pw >= g1.z);
-                            if (cd) {
-                                const float alpha = fminf(0.99f, g1.y * expf(pw));
-                                if (!(alpha < 1.0f / 255.0f)) {
-                                    const float test_T = T * (1 - alpha);
-                                    if (test_T < 0.0001f) {
-                                        done = true;
-                                    } else {
-                                        wq[i] = alpha * T;
-                                        T = test_T;
-                                        last_contributor = (uint32_t)(b * TCF_BATCH + 32 * half + jj + 1);
-                                    }
-                                }
+            for (int i = 0; i < 4; i++) {
+                wq[i] = 0.f;
+                const uint32_t e = (ent >> (8 * i)) & 0xffu;
+                if (e & 0x80u) {                                                       // warp-uniform: candidate of this warp's block
+                    const int jj = (int)(e & 0x3fu);
+                    const float4 g0 = gp[2 * jj];
+                    const float4 g1 = gp[2 * jj + 1];
+                    const float dx = g0.x - pixx, dy = g0.y - pixy;
+                    const float pw = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
+                    const bool cd = !done && !(pw > 0.0f) && (pw >= g1.z);
+                    if (cd) {
+                        const float alpha = fminf(0.99f, g1.y * expf(pw));
+                        if (!(alpha < 1.0f / 255.0f)) {
+                            const float test_T = T * (1 - alpha);
+                            if (test_T < 0.0001f) {
+                                done = true;
+                            } else {
+                                wq[i] = alpha * T;
+                                T = test_T;
+                                last_contributor = (uint32_t)(b * TCF_BATCH + jj + 1);
                             }
                         }
                     }
                 }
-                // operand tiles: wait until the previous issue's MMAs have consumed them before the first rewrite
-                if (nslot == 0 && n_issued > 0) tc::mbar_wait(&sm.mbar[grp], (n_issued - 1) & 1);
-                {
-                    float4 h, l;
-                    h.x = tc::tf32_hi(wq[0]); l.x = wq[0] - h.x;
-                    h.y = tc::tf32_hi(wq[1]); l.y = wq[1] - h.y;
-                    h.z = tc::tf32_hi(wq[2]); l.z = wq[2] - h.z;
-                    h.w = tc::tf32_hi(wq[3]); l.w = wq[3] - h.w;
-                    *reinterpret_cast<float4*>(Ah + (nslot >> 2) * 512) = h;
-                    *reinterpret_cast<float4*>(Al + (nslot >> 2) * 512) = l;
-                    // unused slots of a half's last chunk take any staged row: their weight is 0 and the row is finite
-                    const float f = fp[jsel * TCF_N];
-                    const float fh = tc::tf32_hi(f);
-                    Bh[(nslot >> 2) * 128] = fh;
-                    Bl[(nslot >> 2) * 128] = f - fh;
-                }
-                nslot += 4;
-                if (nslot == TCF_SUB) issue_mma();
             }
+            // operand tiles: wait until the previous issue's MMAs have consumed them before the first rewrite
+            if (nslot == 0 && n_issued > 0) tc::mbar_wait(&sm.mbar[grp], (n_issued - 1) & 1);
+            {
+                float4 h, l;
+                h.x = tc::tf32_hi(wq[0]); l.x = wq[0] - h.x;
+                h.y = tc::tf32_hi(wq[1]); l.y = wq[1] - h.y;
+                h.z = tc::tf32_hi(wq[2]); l.z = wq[2] - h.z;
+                h.w = tc::tf32_hi(wq[3]); l.w = wq[3] - h.w;
+                *reinterpret_cast<float4*>(Ah + (nslot >> 2) * 512) = h;
+                *reinterpret_cast<float4*>(Al + (nslot >> 2) * 512) = l;
+                // this lane transposes channel b_ch of the splat in slot (lane & 3); padded slots read a finite staged row
+                const int jsel = (int)((ent >> (8 * b_slot)) & 0x3fu);
+                const float f = fp[jsel * TCF_N];
+                const float fh = tc::tf32_hi(f);
+                Bh[(nslot >> 2) * 128] = fh;
+                Bl[(nslot >> 2) * 128] = f - fh;
+            }
+            nslot += 4;
+            if (nslot == TCF_SUB) issue_mma();
         }
 
         if (have_next_id) sm.ids[b & 1][tid] = next_id;
