@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "cp_async.cuh"
 #include "candidate.cuh"
+#include "mma.cuh"
 
 namespace sagars {
 
@@ -51,27 +52,6 @@ struct BmSmem {
     uint32_t ids[3][BM_NB];
     uint32_t warp_max[8];                           // deepest contributing list position per warp
 };
-
-__device__ __forceinline__ uint32_t f2tf32(float x)
-{
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-// x = hi + lo with hi exact in tf32 (truncation) and lo = x - hi exact in fp32; the tensor core reads the top 19 bits
-// of lo, so hi*hi' + hi*lo' + lo*hi' carries ~2^-21 relative error (cvt.rna.tf32 would cost ~5 instructions each)
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo)
-{
-    hi = __float_as_uint(x) & 0xFFFFE000u;
-    lo = __float_as_uint(x - __uint_as_float(hi));
-}
-// D(16x8, f32) += A(16x8, tf32, row) * B(8x8, tf32, col)
-__device__ __forceinline__ void mma_16n8k8(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
-{
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
 
 template <int NQ>
 __device__ __forceinline__ void bm_issue_batch(BmSmem<NQ>& sm, int stage, int idbuf, int cnt, int K, bool vec, bool color,
