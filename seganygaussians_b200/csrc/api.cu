@@ -106,13 +106,6 @@ static cudaEvent_t sync_event()
     }
     return ev;
 }
-// SAGARS_BWD_KERNEL=cta: one CTA per tile (render_backward_mma.cu); default: one warp per CTA (render_backward_warp.cu)
-static int bwd_kernel_choice()
-{
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("SAGARS_BWD_KERNEL"); v = (e && e[0] == 'c') ? 1 : 0; }
-    return v;
-}
 // SAGARS_SYNC=block: cudaStreamSynchronize; default: poll the event
 static int sync_mode()
 {
@@ -426,7 +419,7 @@ int sagars_backward(const sagars_backward_args* a, void* stream_)
         {
             ProfScope ps(ST_RENDER_BWD, s);
             if (a->flags & SAGARS_FLAG_NO_TENSOR_CORES) rc = launch_render_backward(*a, d, g, im, point_list, ggrad, s, debug);
-            else if (bwd_kernel_choice() == 1) rc = launch_render_backward_mma(*a, d, g, im, point_list, ggrad, s, debug);
+            else if (a->flags & SAGARS_FLAG_BWD_TILE) rc = launch_render_backward_mma(*a, d, g, im, point_list, ggrad, s, debug);
             else rc = launch_render_backward_warp(*a, d, g, im, point_list, ggrad, s, debug);
         }
         if (rc) return rc;

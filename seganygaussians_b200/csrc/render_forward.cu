@@ -18,6 +18,7 @@
 // The per-pixel arithmetic (power, alpha, the 1/255 and 1e-4 tests, the order of accumulation)
 // is kept operation for operation so that n_contrib / final_T / colours match the reference.
 #include "common.cuh"
+#include <cstdlib>
 #include "cp_async.cuh"
 
 namespace sagars {
@@ -257,9 +258,14 @@ int launch_render_forward(const sagars_forward_args& a, const Dims& d, GeomView 
     const float* features = a.colors_precomp != nullptr ? a.colors_precomp : g.rgb;
     const int K = d.C;
     if (mask_only) return launch_fwd_t<1, false, true, false>(a, d, g, im, point_list, features, s, debug);
-    // K = 32 feature rendering: the channel contraction runs on tcgen05 (render_forward_tc.cu)
-    if (K == 32 && !md && a.colors_precomp != nullptr && !(a.flags & SAGARS_FLAG_NO_TENSOR_CORES))
-        return launch_render_forward_tc(a, d, g, im, point_list, s, debug);
+    // colour-only rendering with the channel contraction on the tensor cores: K = 32 runs the tile-per-CTA tcgen05 / TMEM
+    // kernel (render_forward_tc.cu); SAGARS_FLAG_FWD_WARP selects the warp-per-block mma.sync kernel for any channel count
+    // (render_forward_warp.cu).  Everything else (DEPTH, other channel counts, SAGARS_FLAG_NO_TENSOR_CORES) is the fp32
+    // SIMT kernel below, whose colours are bit-identical to the reference's.
+    if (!md && !(a.flags & SAGARS_FLAG_NO_TENSOR_CORES)) {
+        if (a.flags & SAGARS_FLAG_FWD_WARP) return launch_render_forward_warp(a, d, g, im, point_list, s, debug);
+        if (K == 32 && a.colors_precomp != nullptr) return launch_render_forward_tc(a, d, g, im, point_list, s, debug);
+    }
     const bool vec = (K % 4) == 0;
     const int nq = (K + 3) / 4;
 #define SAGARS_FWD_CASE(NQ_)                                                                               \

@@ -100,11 +100,17 @@ def _flags(settings: GaussianRasterizationSettings, extra: int = 0) -> int:
         f |= _lib.FLAG_CUB_SORT
     if not _USE_TENSOR_CORES:
         f |= _lib.FLAG_NO_TENSOR_CORES
+    if _FORWARD_KERNEL == "warp":
+        f |= _lib.FLAG_FWD_WARP
+    if _BACKWARD_KERNEL == "tile":
+        f |= _lib.FLAG_BWD_TILE
     return f
 
 
 _USE_CUB_SORT = False
 _USE_TENSOR_CORES = True
+_FORWARD_KERNEL = "default"    # "default": tcgen05 tile kernel at K = 32, fp32 SIMT otherwise; "warp": mma.sync warp kernel
+_BACKWARD_KERNEL = "default"   # "default": one warp per 8x4 pixel block; "tile": one CTA per 16x16 tile
 _SPECULATIVE_BINNING = True
 # (device index, P, W, H) -> largest instance count seen so far: the next forward of that shape asks for a binning
 # buffer 25 % larger than this BEFORE the count is known (include/sagars.h, `binning_capacity_hint`)
@@ -125,6 +131,14 @@ def set_tensor_cores(enabled: bool) -> None:
     """Route the K=32 blend through tcgen05 (default) or through the fp32 SIMT kernels (bit-exact colours)."""
     global _USE_TENSOR_CORES
     _USE_TENSOR_CORES = bool(enabled)
+
+
+def set_blend_kernels(forward: str = "default", backward: str = "default") -> None:
+    """Select between the tensor-core blend kernel variants (all give the same results to fp32 rounding)."""
+    global _FORWARD_KERNEL, _BACKWARD_KERNEL
+    if forward not in ("default", "warp") or backward not in ("default", "tile"):
+        raise ValueError("forward in {'default', 'warp'}, backward in {'default', 'tile'}")
+    _FORWARD_KERNEL, _BACKWARD_KERNEL = forward, backward
 
 
 def set_cub_sort(enabled: bool) -> None:

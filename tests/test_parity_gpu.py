@@ -154,11 +154,13 @@ def test_channel_independence_k32_vs_k3():
     """X1: the first three channels of a K=32 render equal the K=3 render of those channels, bit for bit."""
     sc = synthetic.scene(50000, 270, 480, 32)
     c32, r32, _ = _render(sc, 32, tensor_cores=False)
-    c3, r3, _ = _render(sc, 3, colors=sc.gauss.colors[:, :3].contiguous())
+    c3, r3, _ = _render(sc, 3, colors=sc.gauss.colors[:, :3].contiguous(), tensor_cores=False)
     assert torch.equal(c32[:3], c3) and torch.equal(r32, r3)
-    # and the tensor-core path agrees with it to fp32 rounding (3xTF32)
+    # and the tensor-core paths agree with it to fp32 rounding (3xTF32), at both channel counts
     c32_tc, _, _ = _render(sc, 32, tensor_cores=True)
     assert float((c32_tc - c32).abs().max()) <= 1e-5 * float(c32.abs().max())
+    c3_tc, _, _ = _render(sc, 3, colors=sc.gauss.colors[:, :3].contiguous(), tensor_cores=True)
+    assert float((c3_tc - c3).abs().max()) <= 1e-5 * float(c3.abs().max())
 
 
 def test_backward_linearity_full_gradient():
@@ -266,3 +268,27 @@ def test_speculative_binning_matches_exact_layout():
         ok, report = common.compare(other, exact, ints=common.INT_FWD + ("keys",), floats=common.FLOAT_FWD + common.GRADS)
         assert ok, report
         assert np.array_equal(other.color, exact.color)
+
+
+@pytest.mark.parametrize("cfg", [("cf", 6000, 120, 168, 32, False), ("base", 4000, 90, 130, 3, False),
+                                 ("k16", 2500, 80, 96, 16, False), ("k64", 1500, 64, 80, 64, False), ("k5", 1500, 64, 80, 5, False),
+                                 ("depth", 4000, 90, 130, 3, True)],
+                         ids=lambda c: c[0])
+def test_blend_kernel_variants_agree(cfg):
+    """Every shipped blend-kernel variant (forward: tcgen05 tile / mma.sync warp / fp32 SIMT; backward: warp-per-block /
+    CTA-per-tile / fp32 SIMT) gives the same integer state and the same fp32 results within the parity tolerance."""
+    from seganygaussians_b200 import rasterizer as R
+    name, P, H, W, K, depth = cfg
+    sc = synthetic.scene(P, H, W, K)
+    try:
+        base = common.run_torch_impl("ours", sc, K, depth=depth, tensor_cores=False)       # fp32 SIMT forward + backward
+        runs = {}
+        for fwd in ("default", "warp"):
+            for bwd in ("default", "tile"):
+                R.set_blend_kernels(forward=fwd, backward=bwd)
+                runs[(fwd, bwd)] = common.run_torch_impl("ours", sc, K, depth=depth, tensor_cores=True)
+    finally:
+        R.set_blend_kernels()
+    for key, other in runs.items():
+        ok, report = common.compare(other, base, ints=common.INT_FWD, floats=common.FLOAT_FWD + common.GRADS)
+        assert ok, (key, report)
