@@ -140,10 +140,17 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if a.impl == "reference" and world > 1 and rank != 0:
-        return 0   # the reference is single-GPU: rank 0 alone runs it
+    # Reference arm under torchrun: the reference's rasterizer is a CUDA extension, so it gets the same treatment as ours
+    # (one camera per rank + the all-reduce of dL_dcolors, i.e. what train_contrastive_feature.py would do under DDP).
+    # Only the CPU-port fallback (no oracle/_ref on this box) runs on rank 0 alone.
+    ref_is_cuda = False
+    if a.impl == "reference":
+        from tests import common as _c
+        ref_is_cuda = _c.have_ref("cf") and K == 32
+        if world > 1 and rank != 0 and not ref_is_cuda:
+            return 0
     import torch.distributed as dist
-    use_dist = world > 1 and a.impl == "ours"
+    use_dist = world > 1 and (a.impl == "ours" or ref_is_cuda)
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if use_dist:
@@ -275,7 +282,7 @@ def main():
     T_tiles = ((W + 15) // 16) * ((H + 15) // 16)
     line = {
         "metric": "fwd+bwd Gaussians*pixels/s @K=32", "value": value, "unit": "Gaussian*pixel/s",
-        "n_gpus": a.gpus if a.impl == "ours" else world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "n_gpus": world if (use_dist or a.impl != "ours") else a.gpus, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "impl": a.impl,
