@@ -217,7 +217,7 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
                     last_s = s;
                     float dL_dalpha = (s - acc_r) * T;
                     last_alpha = alpha;
-                    dL_dalpha += (-T_final / (1.f - alpha)) * bgdot;
+                    if (bgdot != 0.f) dL_dalpha += (-T_final / (1.f - alpha)) * bgdot;   // zero background: the term is exactly 0
                     w = alpha * T;
                     q = G * dL_dalpha;
                 }
