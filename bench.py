@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fwd-kernel", default="default", choices=["default", "warp"], help="developer A/B switch (rasterizer.set_blend_kernels)")
+    ap.add_argument("--fwd-kernel", default="default", choices=["default", "tile"], help="developer A/B switch (rasterizer.set_blend_kernels)")
     ap.add_argument("--bwd-kernel", default="default", choices=["default", "tile"], help="developer A/B switch")
     return ap.parse_args()
 
@@ -290,7 +290,7 @@ def main():
                    "parallelism": f"camera-dp{n_used}" + ("+allreduce(dL_dcolors)" if use_dist else ""),
                    "l2": "inputs_exceed_l2 (features 128 MB + upstream gradient 265 MB + image 265 MB >> 126 MB L2)",
                    "P_visible": radii_vis, "R_instances": R_inst,
-                   "kernels": {"forward": "tcgen05 tile kernel" if a.fwd_kernel == "default" else "mma.sync warp kernel",
+                   "kernels": {"forward": "mma.sync warp kernel" if a.fwd_kernel == "default" else "tcgen05 tile kernel",
                                "backward": "mma.sync warp kernel" if a.bwd_kernel == "default" else "mma.sync tile kernel"},
                    "S_pair_tests": None},
         "e2e": {"value": e2e_value, "unit": "Gaussian*pixel/s", "ms_per_step": ms_e2e / a.steps,

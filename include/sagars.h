@@ -67,10 +67,12 @@ enum {
 #define SAGARS_FLAG_MASK_ONLY 8u     /* DEPTH mask-only path (forward_mask / mask_forward)            */
 #define SAGARS_FLAG_CUB_SORT 16u     /* use cub::DeviceRadixSort instead of the library's own sort    */
 #define SAGARS_FLAG_NO_TENSOR_CORES 32u /* force the fp32 SIMT blend kernels (bit-exact colours) instead of the tensor-core ones */
-#define SAGARS_FLAG_FWD_WARP 64u     /* forward: one warp per 8x4 pixel block with mma.sync (any channel count) instead of
-                                        the default (tcgen05 tile kernel at C = 32, fp32 SIMT otherwise)               */
+#define SAGARS_FLAG_FWD_TILE 64u     /* forward at C = 32: tile-per-CTA tcgen05 / TMEM kernel (render_forward_tc.cu) instead of
+                                        the default warp-per-block mma.sync kernel (render_forward_warp.cu)              */
 #define SAGARS_FLAG_BWD_TILE 128u    /* backward: one CTA per 16x16 tile (render_backward_mma.cu) instead of the default
                                         one warp per 8x4 pixel block (render_backward_warp.cu)                          */
+#define SAGARS_FLAG_FWD_WARP_ANY 256u /* forward: the warp-per-block tensor-core kernel for every colour-only channel count
+                                        (default: only C = 32; other counts use the fp32 SIMT kernel, bit-exact colours)  */
 
 /* Allocator callback: return a device pointer to at least `bytes` bytes (256-B aligned), or NULL.
  * Replaces: std::function<char*(size_t)> geometryBuffer / binningBuffer / imageBuffer

@@ -22,8 +22,9 @@ FLAG_MASK_DEPTH = 4
 FLAG_MASK_ONLY = 8
 FLAG_CUB_SORT = 16
 FLAG_NO_TENSOR_CORES = 32
-FLAG_FWD_WARP = 64
+FLAG_FWD_TILE = 64
 FLAG_BWD_TILE = 128
+FLAG_FWD_WARP_ANY = 256
 
 ERROR_NAMES = {0: "OK", 1: "EINVAL", 2: "ECUDA", 3: "ENOCOLOR", 4: "EALLOC", 5: "EPREFILTER"}
 

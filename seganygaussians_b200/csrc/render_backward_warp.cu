@@ -50,7 +50,7 @@ struct BwSmem {
 // NQ : float4 groups covering the gradient channels (K colour channels [+ 1 mask channel when MD])
 // VEC: K % 4 == 0 and no mask channel -> feature rows are read as float4
 template <int NQ, bool VEC, bool MD, bool COLOR>
-__global__ void __launch_bounds__(32, (NQ <= 8) ? 24 : 12)
+__global__ void __launch_bounds__(32, (NQ <= 8) ? 28 : 12)
 render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                             int W, int H, int K,
                             const float* __restrict__ bg, const float* __restrict__ geo,

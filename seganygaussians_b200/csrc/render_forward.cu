@@ -258,13 +258,17 @@ int launch_render_forward(const sagars_forward_args& a, const Dims& d, GeomView 
     const float* features = a.colors_precomp != nullptr ? a.colors_precomp : g.rgb;
     const int K = d.C;
     if (mask_only) return launch_fwd_t<1, false, true, false>(a, d, g, im, point_list, features, s, debug);
-    // colour-only rendering with the channel contraction on the tensor cores: K = 32 runs the tile-per-CTA tcgen05 / TMEM
-    // kernel (render_forward_tc.cu); SAGARS_FLAG_FWD_WARP selects the warp-per-block mma.sync kernel for any channel count
-    // (render_forward_warp.cu).  Everything else (DEPTH, other channel counts, SAGARS_FLAG_NO_TENSOR_CORES) is the fp32
-    // SIMT kernel below, whose colours are bit-identical to the reference's.
+    // colour-only rendering with the channel contraction on the tensor cores.  K = 32 (SAGA's feature rendering): the
+    // warp-per-block mma.sync kernel (render_forward_warp.cu), or with SAGARS_FLAG_FWD_TILE the tile-per-CTA tcgen05 / TMEM
+    // kernel (render_forward_tc.cu); SAGARS_FLAG_FWD_WARP_ANY extends the warp kernel to every channel count.  Everything
+    // else (DEPTH, other channel counts, SAGARS_FLAG_NO_TENSOR_CORES) is the fp32 SIMT kernel below, whose colours are
+    // bit-identical to the reference's.
     if (!md && !(a.flags & SAGARS_FLAG_NO_TENSOR_CORES)) {
-        if (a.flags & SAGARS_FLAG_FWD_WARP) return launch_render_forward_warp(a, d, g, im, point_list, s, debug);
-        if (K == 32 && a.colors_precomp != nullptr) return launch_render_forward_tc(a, d, g, im, point_list, s, debug);
+        if (K == 32 && a.colors_precomp != nullptr) {
+            if (a.flags & SAGARS_FLAG_FWD_TILE) return launch_render_forward_tc(a, d, g, im, point_list, s, debug);
+            return launch_render_forward_warp(a, d, g, im, point_list, s, debug);
+        }
+        if (a.flags & SAGARS_FLAG_FWD_WARP_ANY) return launch_render_forward_warp(a, d, g, im, point_list, s, debug);
     }
     const bool vec = (K % 4) == 0;
     const int nq = (K + 3) / 4;

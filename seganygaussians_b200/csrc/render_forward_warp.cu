@@ -45,7 +45,7 @@ struct FwSmem {
 
 // NQ : float4 groups covering the K colour channels;  VEC: K % 4 == 0 -> feature rows are read as float4
 template <int NQ, bool VEC>
-__global__ void __launch_bounds__(32, (NQ <= 8) ? 24 : 12)
+__global__ void __launch_bounds__(32, (NQ <= 8) ? 28 : 12)
 render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int K,
                            const float* __restrict__ geo, const float* __restrict__ features, const float* __restrict__ bg,
                            float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color)

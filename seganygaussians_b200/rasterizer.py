@@ -100,8 +100,10 @@ def _flags(settings: GaussianRasterizationSettings, extra: int = 0) -> int:
         f |= _lib.FLAG_CUB_SORT
     if not _USE_TENSOR_CORES:
         f |= _lib.FLAG_NO_TENSOR_CORES
-    if _FORWARD_KERNEL == "warp":
-        f |= _lib.FLAG_FWD_WARP
+    if _FORWARD_KERNEL == "tile":
+        f |= _lib.FLAG_FWD_TILE
+    elif _FORWARD_KERNEL == "warp_any":
+        f |= _lib.FLAG_FWD_WARP_ANY
     if _BACKWARD_KERNEL == "tile":
         f |= _lib.FLAG_BWD_TILE
     return f
@@ -109,7 +111,8 @@ def _flags(settings: GaussianRasterizationSettings, extra: int = 0) -> int:
 
 _USE_CUB_SORT = False
 _USE_TENSOR_CORES = True
-_FORWARD_KERNEL = "default"    # "default": tcgen05 tile kernel at K = 32, fp32 SIMT otherwise; "warp": mma.sync warp kernel
+_FORWARD_KERNEL = "default"    # "default": mma.sync warp kernel at K = 32, fp32 SIMT otherwise; "tile": tcgen05 tile kernel at
+                               # K = 32; "warp_any": the warp kernel for every colour-only channel count
 _BACKWARD_KERNEL = "default"   # "default": one warp per 8x4 pixel block; "tile": one CTA per 16x16 tile
 _SPECULATIVE_BINNING = True
 # (device index, P, W, H) -> largest instance count seen so far: the next forward of that shape asks for a binning
@@ -128,7 +131,7 @@ def set_speculative_binning(enabled: bool) -> None:
 
 
 def set_tensor_cores(enabled: bool) -> None:
-    """Route the K=32 blend through tcgen05 (default) or through the fp32 SIMT kernels (bit-exact colours)."""
+    """Route the K=32 blend through the tensor cores (default) or through the fp32 SIMT kernels (bit-exact colours)."""
     global _USE_TENSOR_CORES
     _USE_TENSOR_CORES = bool(enabled)
 
@@ -136,8 +139,8 @@ def set_tensor_cores(enabled: bool) -> None:
 def set_blend_kernels(forward: str = "default", backward: str = "default") -> None:
     """Select between the tensor-core blend kernel variants (all give the same results to fp32 rounding)."""
     global _FORWARD_KERNEL, _BACKWARD_KERNEL
-    if forward not in ("default", "warp") or backward not in ("default", "tile"):
-        raise ValueError("forward in {'default', 'warp'}, backward in {'default', 'tile'}")
+    if forward not in ("default", "tile", "warp_any") or backward not in ("default", "tile"):
+        raise ValueError("forward in {'default', 'tile', 'warp_any'}, backward in {'default', 'tile'}")
     _FORWARD_KERNEL, _BACKWARD_KERNEL = forward, backward
 
 

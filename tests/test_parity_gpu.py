@@ -275,7 +275,7 @@ def test_speculative_binning_matches_exact_layout():
                                  ("depth", 4000, 90, 130, 3, True)],
                          ids=lambda c: c[0])
 def test_blend_kernel_variants_agree(cfg):
-    """Every shipped blend-kernel variant (forward: tcgen05 tile / mma.sync warp / fp32 SIMT; backward: warp-per-block /
+    """Every shipped blend-kernel variant (forward: mma.sync warp / tcgen05 tile / fp32 SIMT; backward: warp-per-block /
     CTA-per-tile / fp32 SIMT) gives the same integer state and the same fp32 results within the parity tolerance."""
     from seganygaussians_b200 import rasterizer as R
     name, P, H, W, K, depth = cfg
@@ -283,7 +283,7 @@ def test_blend_kernel_variants_agree(cfg):
     try:
         base = common.run_torch_impl("ours", sc, K, depth=depth, tensor_cores=False)       # fp32 SIMT forward + backward
         runs = {}
-        for fwd in ("default", "warp"):
+        for fwd in ("default", "tile", "warp_any"):
             for bwd in ("default", "tile"):
                 R.set_blend_kernels(forward=fwd, backward=bwd)
                 runs[(fwd, bwd)] = common.run_torch_impl("ours", sc, K, depth=depth, tensor_cores=True)
