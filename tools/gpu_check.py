@@ -96,28 +96,34 @@ def sort_check():
     return ok_all
 
 
-def timing(P, H, W, K, iters=10):
-    section(f"timing: P={P} {H}x{W} K={K}")
+def timing(P, H, W, K, iters=10, depth=False, use_sh=False, deg=0, M=0):
+    section(f"timing: P={P} {H}x{W} K={K} depth={depth} sh={use_sh}")
     dev = torch.device("cuda", 0)
-    sc = synthetic.scene(P, H, W, K)
-    variant = common.variant_of(K, False)
+    sc = synthetic.scene(P, H, W, K, sh_coeffs=M)
+    variant = common.variant_of(K, depth)
     from seganygaussians_b200 import rasterizer as R
-    impls = {"ours": (R.GaussianRasterizationSettings, {"base": R.GaussianRasterizer, "cf": R.GaussianRasterizerContrastiveF}[variant])}
+    impls = {"ours": (R.GaussianRasterizationSettings, {"base": R.GaussianRasterizer, "cf": R.GaussianRasterizerContrastiveF,
+                                                        "depth": R.GaussianRasterizerDepth}[variant])}
     if common.have_ref(variant):
         m = common.ref_module(variant)
         impls["ref"] = (m.GaussianRasterizationSettings, m.GaussianRasterizer)
     g = sc.gauss
-    dL = sc.dL_dout.to(dev)
+    dL = sc.dL_dout[:K].to(dev)
     for name, (Settings, Rast) in impls.items():
-        L = common._leafs(sc, dev, False)
-        rs = common._settings(Settings, sc, dev, K, 0)
+        L = common._leafs(sc, dev, use_sh)
+        rs = common._settings(Settings, sc, dev, K, deg)
         rast = Rast(raster_settings=rs)
 
         def step():
-            for t in (L.means3D, L.means2D, L.opacities, L.scales, L.rotations, L.colors):
-                t.grad = None
-            color, radii = rast(means3D=L.means3D, means2D=L.means2D, opacities=L.opacities, shs=None,
-                                colors_precomp=L.colors, scales=L.scales, rotations=L.rotations, cov3D_precomp=None)
+            for t in (L.means3D, L.means2D, L.opacities, L.scales, L.rotations, L.colors, L.shs, getattr(L, "mask", None)):
+                if t is not None:
+                    t.grad = None
+            kw = dict(means3D=L.means3D, means2D=L.means2D, opacities=L.opacities, shs=L.shs,
+                      colors_precomp=L.colors, scales=L.scales, rotations=L.rotations, cov3D_precomp=None)
+            if depth:
+                color, om, od, radii = rast(mask=L.mask, **kw)
+            else:
+                color, radii = rast(**kw)
             return color
 
         for _ in range(3):
@@ -138,6 +144,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--tiny", action="store_true", help="only the smallest parity case (for compute-sanitizer)")
     ap.add_argument("--no-timing", action="store_true")
+    ap.add_argument("--large", action="store_true", help="BASELINE-scale parity + timing of the other configs (c1, c3-like, c5-like)")
     a = ap.parse_args()
     print("device:", torch.cuda.get_device_name(0), "| lib:", _lib.load().sagars_arch().decode())
     results = {}
@@ -145,6 +152,18 @@ if __name__ == "__main__":
         results["tiny_cf"] = parity("tiny_cf", 500, 40, 56, 32, with_ref=False)
         results["tiny_depth"] = parity("tiny_depth", 500, 40, 56, 3, depth=True, with_ref=False)
         print(results)
+        sys.exit(0 if all(results.values()) else 1)
+    if a.large:
+        results["c1"] = parity("c1", 10000, 256, 256, 3, with_oracle=True)
+        results["c3_like"] = parity("c3_like", 5000000, 1036, 1600, 32, with_oracle=False)
+        results["c5_like"] = parity("c5_like", 2000000, 1600, 1600, 3, depth=True, use_sh=True, deg=3, M=16, with_oracle=False)
+        timing(10000, 256, 256, 3)
+        timing(5000000, 1036, 1600, 32, iters=5)
+        timing(2000000, 1600, 1600, 3, iters=5, depth=True, use_sh=True, deg=3, M=16)
+        timing(1000000, 1080, 1920, 3, iters=5)
+        section("summary")
+        for k, v in results.items():
+            print(f"  {k:14s} {'OK' if v else 'FAIL'}")
         sys.exit(0 if all(results.values()) else 1)
     results["sort"] = sort_check()
     results["cf_small"] = parity("cf_small", 3000, 72, 104, 32)

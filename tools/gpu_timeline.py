@@ -27,14 +27,29 @@ def main():
     rast = R.GaussianRasterizerContrastiveF(raster_settings=rs)
     marks = []
 
+    e2e = "--e2e" in sys.argv
+    view_h, proj_h, campos_h, bg_h = (t.clone().pin_memory() for t in (c.world_view_transform, c.full_proj_transform,
+                                                                        c.camera_center, torch.zeros(K)))
+
     def step():
         for t in leaves:
             t.grad = None
         t0 = time.perf_counter()
-        color, radii = rast(means3D=means3D, means2D=means2D, opacities=opac, shs=None, colors_precomp=colors,
-                            scales=scales, rotations=rots, cov3D_precomp=None)
+        if e2e:   # bench.py's end-to-end step: camera from pinned host memory, loss scalar read back
+            r = R.GaussianRasterizerContrastiveF(raster_settings=rs._replace(
+                viewmatrix=view_h.to(dev, non_blocking=True), projmatrix=proj_h.to(dev, non_blocking=True),
+                campos=campos_h.to(dev, non_blocking=True), bg=bg_h.to(dev, non_blocking=True)))
+        else:
+            r = rast
+        color, radii = r(means3D=means3D, means2D=means2D, opacities=opac, shs=None, colors_precomp=colors,
+                         scales=scales, rotations=rots, cov3D_precomp=None)
         t1 = time.perf_counter()
-        color.backward(dL)
+        if e2e:
+            loss = (color * dL).sum()
+            loss.backward()
+            float(loss.item())
+        else:
+            color.backward(dL)
         t2 = time.perf_counter()
         marks.append((t0, t1, t2))
 
