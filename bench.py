@@ -42,6 +42,8 @@ import torch
 WORKLOADS = {
     # BASELINE.json configs[1]
     "c2": dict(P=1_000_000, H=1080, W=1920, K=32, desc="synthetic 1M Gaussians, 1080x1920, K=32 affinity features, 1 camera/GPU, fwd+bwd"),
+    # BASELINE.json configs[2]-like (parity-test case, not the bench line): 5M Gaussians
+    "c3": dict(P=5_000_000, H=1036, W=1600, K=32, desc="synthetic 5M Gaussians, 1036x1600, K=32 (garden-like), 1 camera/GPU, fwd+bwd"),
     # small variant for quick local checks (never a bench line)
     "tiny": dict(P=20_000, H=270, W=480, K=32, desc="tiny smoke workload"),
 }
