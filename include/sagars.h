@@ -230,6 +230,20 @@ SAGARS_API int sagars_sort_pairs(int32_t device, int32_t n, int32_t end_bit,
                       uint64_t* keys_out, uint32_t* vals_out,
                       void* temp, int32_t use_cub, void* stream);
 
+/* Exact K nearest neighbours (squared Euclidean distance, ascending) of every query in a reference cloud, on a uniform
+ * grid; runs on `stream` without host synchronisation.  `queries == NULL` (or == points): the cloud against itself.
+ * `exclude_self` (cloud against itself only): point i is never its own neighbour.  Outputs are optional:
+ * idx_out [Q,K] (-1 where the cloud has fewer than K eligible points), dist2_out [Q,K], mean_dist2_out [Q] = mean of the
+ * K distances.  1 <= K <= 32.  `temp`: sagars_knn_temp_bytes(num_points) bytes of device scratch.
+ * Replaces (imports the reference's scripts need to start):
+ *   simple_knn._C.distCUDA2  -- submodules/simple-knn/simple_knn.cu:146-219 (K = 3, exclude_self, mean_dist2_out;
+ *                               same distance expression and summation order, results equal to fp32 rounding);
+ *   pytorch3d.ops.knn_points -- call sites scene/gaussian_model_ff.py:326-331, 345-350 (K = 16, self included). */
+SAGARS_API size_t sagars_knn_temp_bytes(int32_t num_points);
+SAGARS_API int sagars_knn(int32_t device, int32_t num_points, const float* points /* [N,3] */,
+                          int32_t num_queries, const float* queries /* [Q,3] or NULL */, int32_t K, int32_t exclude_self,
+                          int64_t* idx_out, float* dist2_out, float* mean_dist2_out, void* temp, void* stream);
+
 /* number of kernels launched by this library (process-wide) since the last reset
  * (bench.py reports it as `gpu_launches`). */
 SAGARS_API int64_t sagars_launch_count(void);

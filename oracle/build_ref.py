@@ -44,6 +44,9 @@ SOURCES = [
     "rasterize_points.cu",
     "ext.cpp",
 ]
+# the reference's 3-nearest-neighbour extension (oracle for the sagars_knn shim)
+VARIANTS["simple_knn"] = ("simple-knn", "simple_knn")
+SIMPLE_KNN_SOURCES = ["spatial.cu", "simple_knn.cu", "ext.cpp"]
 
 
 def build_variant(tag: str, verbose: bool = False) -> str:
@@ -59,15 +62,17 @@ def build_variant(tag: str, verbose: bool = False) -> str:
     from torch.utils import cpp_extension
 
     os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+    is_knn = tag == "simple_knn"
     cpp_extension.load(
         name="_C",
-        sources=[os.path.join(src_dir, s) for s in SOURCES],
-        extra_include_paths=[os.path.join(src_dir, "third_party", "glm"), src_dir],
+        sources=[os.path.join(src_dir, s) for s in (SIMPLE_KNN_SOURCES if is_knn else SOURCES)],
+        extra_include_paths=[src_dir] if is_knn else [os.path.join(src_dir, "third_party", "glm"), src_dir],
         extra_cflags=["-O3", "-include", "cstdint"],
         extra_cuda_cflags=[
             "-O3",
             "-gencode", "arch=compute_100a,code=sm_100a",
             "-include", "cstdint",
+            "-include", "cfloat",      # simple_knn.cu uses FLT_MAX without <cfloat>
             "-lineinfo",
         ],
         build_directory=build_dir,
@@ -79,7 +84,11 @@ def build_variant(tag: str, verbose: bool = False) -> str:
         raise RuntimeError(f"build produced no {so}")
     shutil.copy2(so, os.path.join(out_dir, "_C.so"))
     # install the reference's public python API next to the built module (git-ignored output)
-    shutil.copy2(os.path.join(src_dir, pkg, "__init__.py"), os.path.join(out_dir, "__init__.py"))
+    init_src = os.path.join(src_dir, pkg, "__init__.py")
+    if os.path.exists(init_src):
+        shutil.copy2(init_src, os.path.join(out_dir, "__init__.py"))
+    else:   # simple_knn ships an empty package directory; the module is imported as simple_knn._C
+        open(os.path.join(out_dir, "__init__.py"), "w").close()
     return out_dir
 
 

@@ -81,7 +81,7 @@ ABI_SYMBOLS = (
     "sagars_forward", "sagars_backward", "sagars_mark_visible",
     "sagars_geom_bytes", "sagars_image_bytes", "sagars_binning_bytes", "sagars_grad_scratch_bytes",
     "sagars_get_geom_layout", "sagars_get_image_layout", "sagars_get_binning_layout",
-    "sagars_sort_temp_bytes", "sagars_sort_pairs",
+    "sagars_sort_temp_bytes", "sagars_sort_pairs", "sagars_knn_temp_bytes", "sagars_knn",
     "sagars_launch_count", "sagars_reset_launch_count",
     "sagars_profile_enable", "sagars_profile_num_stages", "sagars_profile_stage_name", "sagars_profile_read",
     "sagars_last_error", "sagars_abi_version", "sagars_arch",
@@ -127,6 +127,11 @@ def load() -> C.CDLL:
         for fn in ("sagars_geom_bytes", "sagars_binning_bytes", "sagars_grad_scratch_bytes", "sagars_sort_temp_bytes"):
             getattr(lib, fn).restype = C.c_size_t
             getattr(lib, fn).argtypes = [C.c_int32]
+        lib.sagars_knn_temp_bytes.restype = C.c_size_t
+        lib.sagars_knn_temp_bytes.argtypes = [C.c_int32]
+        lib.sagars_knn.restype = C.c_int
+        lib.sagars_knn.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.sagars_image_bytes.restype = C.c_size_t
         lib.sagars_image_bytes.argtypes = [C.c_int32, C.c_int32]
         lib.sagars_get_geom_layout.argtypes = [C.c_int32, C.POINTER(GeomLayout)]

@@ -478,4 +478,24 @@ int sagars_sort_pairs(int32_t device, int32_t n, int32_t end_bit, const uint64_t
     return SAGARS_OK;
 }
 
+size_t sagars_knn_temp_bytes(int32_t num_points) { return knn_temp_bytes((size_t)(num_points < 0 ? 0 : num_points)); }
+
+int sagars_knn(int32_t device, int32_t num_points, const float* points, int32_t num_queries, const float* queries,
+               int32_t K, int32_t exclude_self, int64_t* idx_out, float* dist2_out, float* mean_dist2_out, void* temp,
+               void* stream)
+{
+    g_err[0] = 0;
+    if (num_points < 0 || num_queries < 0 || K < 1 || K > 32 || (num_points > 0 && (!points || !temp)) ||
+        (exclude_self && queries != nullptr && queries != points)) {
+        set_error("sagars_knn: bad argument (1 <= K <= 32; exclude_self needs queries == points)");
+        return SAGARS_EINVAL;
+    }
+    if (queries == nullptr || queries == points) { queries = nullptr; num_queries = num_points; }
+    if (num_queries == 0) return SAGARS_OK;
+    if (num_points == 0) { set_error("sagars_knn: empty reference cloud"); return SAGARS_EINVAL; }
+    SAGARS_CUDA(cudaSetDevice(device));
+    return launch_knn(num_points, points, num_queries, queries, K, exclude_self != 0, (long long*)idx_out, dist2_out,
+                      mean_dist2_out, temp, (cudaStream_t)stream);
+}
+
 }  // extern "C"

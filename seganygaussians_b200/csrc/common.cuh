@@ -194,6 +194,9 @@ int launch_sort_pairs(const uint32_t* n_dev, int cap, int end_bit, uint64_t* key
                       cudaStream_t s, bool debug);
 int sort_num_passes(int end_bit);
 int launch_tile_ranges(const uint32_t* n_dev, int cap, int num_tiles, const uint64_t* keys, uint2* ranges, cudaStream_t s, bool debug);
+size_t knn_temp_bytes(size_t n);
+int launch_knn(int n, const float* points, int nq, const float* queries, int K, bool exclude_self, long long* idx_out,
+               float* dist_out, float* mean_out, void* temp, cudaStream_t s);
 int launch_render_forward_warp(const sagars_forward_args& a, const Dims& d, GeomView g, ImageView im,
                                const uint32_t* point_list, cudaStream_t s, bool debug);
 int launch_render_forward(const sagars_forward_args& a, const Dims& d, GeomView g, ImageView im,
