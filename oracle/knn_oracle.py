@@ -10,7 +10,7 @@ tools/, never by the product).
 
 Brute force over the full distance matrix in blocks: exact, O(N^2), meant for N up to a few 10^4.
 Pinned by tests/test_knn_oracle.py against golden outputs of the unmodified reference extension
-(tests/golden/simple_knn_*.npz, made on a B200 by tests/golden/make_golden_knn.py) and against scipy's cKDTree."""
+(tests/golden/knn/simple_knn_*.npz, made on a B200 by tests/golden/make_golden_knn.py) and against scipy's cKDTree."""
 import numpy as np
 
 

@@ -2,7 +2,7 @@
 """Golden vectors for the neighbour-search shims: outputs of the UNMODIFIED reference extension ``simple_knn._C.distCUDA2``
 (built by oracle/build_ref.py into oracle/_ref/simple_knn) on seeded point clouds.  Run on a GPU box:
 
-    python tests/golden/make_golden_knn.py gpurun_out/simple_knn_small.npz      # then copy into tests/golden/
+    python tests/golden/make_golden_knn.py gpurun_out/simple_knn_small.npz      # then copy into tests/golden/knn/
 
 The clouds are regenerated from the seeds by tests/knn_cases.py, so only the reference's outputs are stored."""
 import importlib.util

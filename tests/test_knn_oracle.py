@@ -9,7 +9,7 @@ from scipy.spatial import cKDTree
 from oracle import knn_oracle
 from tests import knn_cases
 
-GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "simple_knn_small.npz")
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "knn", "simple_knn_small.npz")
 
 
 @pytest.mark.parametrize("name", list(knn_cases.clouds()))
