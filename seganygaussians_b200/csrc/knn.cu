@@ -1,4 +1,4 @@
-// knn.cu -- exact K nearest neighbours on a uniform grid.
+// knn.cu -- exact K nearest neighbours on Morton-ordered boxes.
 //
 // Serves the two neighbour searches the reference's scripts import from third-party packages that are not installed:
 //   * simple_knn._C.distCUDA2(points)       -> mean squared distance to the 3 nearest OTHER points
@@ -7,50 +7,52 @@
 //   * pytorch3d.ops.knn_points(xyz, xyz, K) -> indices / squared distances of the K nearest points, the point itself
 //       included (scene/gaussian_model_ff.py:326-331, 345-350: K = 16 for the feature smoothing map).
 //
-// Method: bounding box -> cell size chosen on the device so that there are about N/2 cells (never more than N) ->
-// (cell id, point index) pairs sorted with the library's radix sort -> per-cell [first, last) ranges -> one thread
-// per query walks the cells in shells of growing Chebyshev radius r around its own cell, keeps the K best in
-// registers, and stops when the K-th best squared distance is <= (r * cell)^2, the closest anything outside the
-// visited cube can be (or when the cube covers the grid).  Exact for any input, including duplicates and outliers.
-// Everything runs on the caller's stream without host synchronisation.
+// Method (adaptive to the very uneven density of a trained scene -- dense surfaces plus far floaters -- where a uniform
+// grid degenerates): bounding box -> 30-bit Morton codes -> (code, index) pairs sorted with the library's radix sort ->
+// points gathered in Morton order -> axis-aligned bounding boxes of every 128 consecutive points (level 1) and of every
+// 32 level-1 boxes (level 2).  One thread per query, queries taken in Morton order so a warp works on neighbouring
+// points: the K best live in registers; the query's own level-1 box is scanned first (a tight bound at once), then all
+// level-2 boxes are tested against the current K-th best squared distance, surviving ones descend to their level-1
+// boxes, surviving ones are scanned.  A box is skipped only when its distance lower bound exceeds the K-th best, so
+// the result is exact for any input (duplicates, flat or collinear clouds, outliers).  Everything runs on the caller's
+// stream without host synchronisation.
 #include "common.cuh"
 #include <cfloat>
 
 namespace sagars {
 
-struct KnnGrid {
-    float ox, oy, oz;      // grid origin (bounding-box minimum)
-    float h, inv_h;        // cell size
-    int nx, ny, nz;        // grid dimensions, nx * ny * nz <= num_points
-    int ncell;
-};
+constexpr int KNN_L1 = 128;    // points per level-1 box
+constexpr int KNN_FAN = 32;    // level-1 boxes per level-2 box
+
+struct KnnBox { float lo[3], hi[3]; };   // 24 bytes
 
 struct KnnTemp {
     int* bbox;             // 6 ordered-int encoded floats: min xyz, max xyz
-    KnnGrid* grid;
-    uint64_t* keys_a;      // sorted (cell id, point index) pairs land here
+    uint64_t* keys_a;      // sorted (Morton code, point index) pairs land here
     uint64_t* keys_b;
     uint32_t* vals_a;
     uint32_t* vals_b;
     void* sort_temp;
-    uint2* cell_range;     // [num_points] (first, last + 1) in the sorted order, (0, 0) for empty cells
-    float4* sorted_pts;    // (x, y, z, original index as bits) in sorted order
+    float4* sorted_pts;    // (x, y, z, original index as bits) in Morton order
+    KnnBox* box1;          // ceil(n / 128)
+    KnnBox* box2;          // ceil(nbox1 / 32)
 };
 
 static size_t knn_temp_layout(size_t n, KnnTemp* t, char* base)
 {
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes); return base ? base + at : (char*)nullptr; };
+    const size_t nb1 = (n + KNN_L1 - 1) / KNN_L1, nb2 = (nb1 + KNN_FAN - 1) / KNN_FAN;
     char* p;
     p = take(64);      if (t) t->bbox = (int*)p;
-    p = take(64);      if (t) t->grid = (KnnGrid*)p;
     p = take(n * 8);   if (t) t->keys_a = (uint64_t*)p;
     p = take(n * 8);   if (t) t->keys_b = (uint64_t*)p;
     p = take(n * 4);   if (t) t->vals_a = (uint32_t*)p;
     p = take(n * 4);   if (t) t->vals_b = (uint32_t*)p;
     p = take(sort_temp_bytes(n)); if (t) t->sort_temp = (void*)p;
-    p = take(n * 8);   if (t) t->cell_range = (uint2*)p;
     p = take(n * 16);  if (t) t->sorted_pts = (float4*)p;
+    p = take((nb1 + 1) * sizeof(KnnBox)); if (t) t->box1 = (KnnBox*)p;
+    p = take((nb2 + 1) * sizeof(KnnBox)); if (t) t->box2 = (KnnBox*)p;
     return o + 256;
 }
 
@@ -95,98 +97,134 @@ knn_bbox_kernel(int n, const float* __restrict__ pts, int* __restrict__ bbox)
     }
 }
 
-// one thread: cell size for ~n/2 cells, at most n cells and 1024 per axis
-__global__ void knn_grid_setup_kernel(int n, const int* __restrict__ bbox, KnnGrid* __restrict__ g)
+__device__ __forceinline__ uint32_t knn_spread3(uint32_t x)   // 10 bits -> every third bit
 {
-    const float ox = ord2f(bbox[0]), oy = ord2f(bbox[1]), oz = ord2f(bbox[2]);
-    float ex = ord2f(bbox[3]) - ox, ey = ord2f(bbox[4]) - oy, ez = ord2f(bbox[5]) - oz;
-    const float emax = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-30f));
-    // degenerate (flat / collinear) clouds: give the thin axes a small non-zero extent
-    ex = fmaxf(ex, emax * 1e-6f); ey = fmaxf(ey, emax * 1e-6f); ez = fmaxf(ez, emax * 1e-6f);
-    const float target = fmaxf(1.f, 0.5f * (float)n);
-    float h = cbrtf(ex * ey * ez / target);
-    h = fmaxf(h, emax / 1024.f);
-    int nx, ny, nz;
-    for (int it = 0; it < 64; it++) {
-        nx = min(1024, (int)(ex / h) + 1);
-        ny = min(1024, (int)(ey / h) + 1);
-        nz = min(1024, (int)(ez / h) + 1);
-        if ((long long)nx * ny * nz <= (long long)max(n, 1)) break;
-        h *= 1.2599211f;   // halves the cell count
-    }
-    g->ox = ox; g->oy = oy; g->oz = oz;
-    g->h = h; g->inv_h = 1.f / h;
-    g->nx = nx; g->ny = ny; g->nz = nz;
-    g->ncell = nx * ny * nz;
-}
-
-__device__ __forceinline__ void knn_cell_of(const KnnGrid& g, float x, float y, float z, int& cx, int& cy, int& cz)
-{
-    cx = min(g.nx - 1, max(0, (int)((x - g.ox) * g.inv_h)));
-    cy = min(g.ny - 1, max(0, (int)((y - g.oy) * g.inv_h)));
-    cz = min(g.nz - 1, max(0, (int)((z - g.oz) * g.inv_h)));
+    x = (x | (x << 16)) & 0x030000FFu;
+    x = (x | (x << 8)) & 0x0300F00Fu;
+    x = (x | (x << 4)) & 0x030C30C3u;
+    x = (x | (x << 2)) & 0x09249249u;
+    return x;
 }
 
 __global__ void __launch_bounds__(256)
-knn_cell_keys_kernel(int n, const float* __restrict__ pts, const KnnGrid* __restrict__ gp, uint64_t* __restrict__ keys,
-                     uint32_t* __restrict__ vals)
+knn_morton_kernel(int n, const float* __restrict__ pts, const int* __restrict__ bbox, uint64_t* __restrict__ keys,
+                  uint32_t* __restrict__ vals)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const KnnGrid g = *gp;
-    int cx, cy, cz;
-    knn_cell_of(g, pts[3 * (size_t)i], pts[3 * (size_t)i + 1], pts[3 * (size_t)i + 2], cx, cy, cz);
-    keys[i] = (uint64_t)((cz * g.ny + cy) * g.nx + cx);
+    uint32_t code = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float lo = ord2f(bbox[c]), hi = ord2f(bbox[3 + c]);
+        const float ext = hi - lo;
+        const float u = ext > 0.f ? (pts[3 * (size_t)i + c] - lo) / ext : 0.f;
+        const uint32_t q = (uint32_t)fminf(fmaxf(u * 1023.f, 0.f), 1023.f);
+        code |= knn_spread3(q) << c;
+    }
+    keys[i] = (uint64_t)code;
     vals[i] = (uint32_t)i;
 }
 
 __global__ void __launch_bounds__(256)
-knn_ranges_gather_kernel(int n, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                         const float* __restrict__ pts, uint2* __restrict__ cell_range, float4* __restrict__ sorted_pts)
+knn_gather_kernel(int n, const uint32_t* __restrict__ vals, const float* __restrict__ pts, float4* __restrict__ sorted_pts)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t cur = (uint32_t)keys[i];
-    if (i == 0) cell_range[cur].x = 0;
-    else {
-        const uint32_t prev = (uint32_t)keys[i - 1];
-        if (cur != prev) { cell_range[prev].y = (uint32_t)i; cell_range[cur].x = (uint32_t)i; }
-    }
-    if (i == n - 1) cell_range[cur].y = (uint32_t)n;
     const uint32_t j = vals[i];
     sorted_pts[i] = make_float4(pts[3 * (size_t)j], pts[3 * (size_t)j + 1], pts[3 * (size_t)j + 2], __uint_as_float(j));
 }
 
-// One thread per query.  SELF: the query set is the point set and query i may not return point i (simple_knn).
-template <int K, bool SELF>
+// level-1 boxes: one warp per 128 consecutive points
+__global__ void __launch_bounds__(256)
+knn_box1_kernel(int n, const float4* __restrict__ sorted_pts, KnnBox* __restrict__ box1, int nb1)
+{
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= nb1) return;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = b * KNN_L1 + lane; i < min(n, (b + 1) * KNN_L1); i += 32) {
+        const float4 p = sorted_pts[i];
+        lo[0] = fminf(lo[0], p.x); hi[0] = fmaxf(hi[0], p.x);
+        lo[1] = fminf(lo[1], p.y); hi[1] = fmaxf(hi[1], p.y);
+        lo[2] = fminf(lo[2], p.z); hi[2] = fmaxf(hi[2], p.z);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+    if (lane == 0) {
+        KnnBox bx;
+#pragma unroll
+        for (int c = 0; c < 3; c++) { bx.lo[c] = lo[c]; bx.hi[c] = hi[c]; }
+        box1[b] = bx;
+    }
+}
+
+// level-2 boxes: one thread per 32 level-1 boxes
 __global__ void __launch_bounds__(128)
-knn_search_kernel(int nq, const float* __restrict__ queries, const KnnGrid* __restrict__ gp,
-                  const uint2* __restrict__ cell_range, const float4* __restrict__ sorted_pts,
+knn_box2_kernel(const KnnBox* __restrict__ box1, int nb1, KnnBox* __restrict__ box2, int nb2)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb2) return;
+    KnnBox bx;
+#pragma unroll
+    for (int c = 0; c < 3; c++) { bx.lo[c] = FLT_MAX; bx.hi[c] = -FLT_MAX; }
+    for (int i = b * KNN_FAN; i < min(nb1, (b + 1) * KNN_FAN); i++) {
+        const KnnBox a = box1[i];
+#pragma unroll
+        for (int c = 0; c < 3; c++) { bx.lo[c] = fminf(bx.lo[c], a.lo[c]); bx.hi[c] = fmaxf(bx.hi[c], a.hi[c]); }
+    }
+    box2[b] = bx;
+}
+
+// squared distance from a point to a box (0 inside); a lower bound for every point of the box
+__device__ __forceinline__ float knn_box_dist2(const KnnBox& b, float x, float y, float z)
+{
+    const float dx = fmaxf(fmaxf(b.lo[0] - x, x - b.hi[0]), 0.f);
+    const float dy = fmaxf(fmaxf(b.lo[1] - y, y - b.hi[1]), 0.f);
+    const float dz = fmaxf(fmaxf(b.lo[2] - z, z - b.hi[2]), 0.f);
+    return dx * dx + dy * dy + dz * dz;
+}
+
+// One thread per query.  SELF: the query set is the point set (thread t takes the t-th point in Morton order); with
+// EXCL a point is never its own neighbour (simple_knn).  Otherwise thread t takes external query t.
+template <int K, bool SELF, bool EXCL>
+__global__ void __launch_bounds__(128)
+knn_search_kernel(int n, int nq, const float* __restrict__ queries, const float4* __restrict__ sorted_pts,
+                  const KnnBox* __restrict__ box1, int nb1, const KnnBox* __restrict__ box2, int nb2,
                   int k_out, long long* __restrict__ idx_out, float* __restrict__ dist_out, float* __restrict__ mean_out)
 {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
-    const KnnGrid g = *gp;
-    const float qx = queries[3 * (size_t)q], qy = queries[3 * (size_t)q + 1], qz = queries[3 * (size_t)q + 2];
-    int cx, cy, cz;
-    knn_cell_of(g, qx, qy, qz, cx, cy, cz);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nq) return;
+    float qx, qy, qz;
+    uint32_t qid;            // output row (original index of the query)
+    int own1 = -1;           // the query's own level-1 box (SELF)
+    if (SELF) {
+        const float4 p = sorted_pts[t];
+        qx = p.x; qy = p.y; qz = p.z; qid = __float_as_uint(p.w);
+        own1 = t / KNN_L1;
+    } else {
+        qx = queries[3 * (size_t)t]; qy = queries[3 * (size_t)t + 1]; qz = queries[3 * (size_t)t + 2];
+        qid = (uint32_t)t;
+    }
 
     float bd[K];
     uint32_t bi[K];
 #pragma unroll
     for (int j = 0; j < K; j++) { bd[j] = FLT_MAX; bi[j] = 0xffffffffu; }
 
-    auto visit_cell = [&](int x, int y, int z) {
-        const uint2 r = cell_range[(z * g.ny + y) * g.nx + x];
-        for (uint32_t i = r.x; i < r.y; i++) {
+    auto scan_box1 = [&](int b) {
+        const int e = min(n, (b + 1) * KNN_L1);
+        for (int i = b * KNN_L1; i < e; i++) {
             const float4 p = sorted_pts[i];
-            const uint32_t pid = __float_as_uint(p.w);
-            if (SELF && pid == (uint32_t)q) continue;
-            // same expression as simple_knn.cu:135-137 (d = candidate - query), so nvcc contracts it the same way
+            if (EXCL && i == t) continue;
+            // same expression as simple_knn.cu:135-137 (d = candidate - query)
             const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
             float d = dx * dx + dy * dy + dz * dz;
             if (!(d < bd[K - 1])) continue;
-            uint32_t id = pid;
+            uint32_t id = __float_as_uint(p.w);
 #pragma unroll
             for (int j = 0; j < K; j++) {
                 if (bd[j] > d) {
@@ -197,34 +235,23 @@ knn_search_kernel(int nq, const float* __restrict__ queries, const KnnGrid* __re
         }
     };
 
-    const int rmax = max(max(cx, g.nx - 1 - cx), max(max(cy, g.ny - 1 - cy), max(cz, g.nz - 1 - cz)));
-    for (int r = 0; r <= rmax; r++) {
-        const int z0 = max(0, cz - r), z1 = min(g.nz - 1, cz + r);
-        const int y0 = max(0, cy - r), y1 = min(g.ny - 1, cy + r);
-        for (int z = z0; z <= z1; z++) {
-            const bool zface = (z == cz - r) || (z == cz + r);
-            for (int y = y0; y <= y1; y++) {
-                const bool yface = (y == cy - r) || (y == cy + r);
-                if (zface || yface) {
-                    const int x0 = max(0, cx - r), x1 = min(g.nx - 1, cx + r);
-                    for (int x = x0; x <= x1; x++) visit_cell(x, y, z);
-                } else {
-                    if (cx - r >= 0) visit_cell(cx - r, y, z);
-                    if (r > 0 && cx + r <= g.nx - 1) visit_cell(cx + r, y, z);
-                }
-            }
+    if (SELF) scan_box1(own1);
+    for (int b2 = 0; b2 < nb2; b2++) {
+        if (knn_box_dist2(box2[b2], qx, qy, qz) > bd[K - 1]) continue;
+        const int e1 = min(nb1, (b2 + 1) * KNN_FAN);
+        for (int b1 = b2 * KNN_FAN; b1 < e1; b1++) {
+            if (b1 == own1) continue;
+            if (knn_box_dist2(box1[b1], qx, qy, qz) > bd[K - 1]) continue;
+            scan_box1(b1);
         }
-        // everything outside the visited cube is at least r * h away from the query (it lies inside its own cell)
-        const float reach = (float)r * g.h * 0.9999f;   // margin for the rounding of the cell assignment
-        if (bd[K - 1] <= reach * reach) break;
     }
 
     if (idx_out || dist_out) {
 #pragma unroll
         for (int j = 0; j < K; j++) {
             if (j < k_out) {
-                if (idx_out) idx_out[(size_t)q * k_out + j] = (bi[j] == 0xffffffffu) ? -1ll : (long long)bi[j];
-                if (dist_out) dist_out[(size_t)q * k_out + j] = bd[j];
+                if (idx_out) idx_out[(size_t)qid * k_out + j] = (bi[j] == 0xffffffffu) ? -1ll : (long long)bi[j];
+                if (dist_out) dist_out[(size_t)qid * k_out + j] = bd[j];
             }
         }
     }
@@ -234,17 +261,21 @@ knn_search_kernel(int nq, const float* __restrict__ queries, const KnnGrid* __re
 #pragma unroll
         for (int j = 0; j < K; j++)
             if (j < k_out) sacc += bd[j];
-        mean_out[q] = sacc / (float)k_out;
+        mean_out[qid] = sacc / (float)k_out;
     }
 }
 
 template <int K>
-static void knn_launch_search(bool self, int nq, const float* queries, const KnnTemp& t, int k_out, long long* idx_out,
-                              float* dist_out, float* mean_out, cudaStream_t s)
+static void knn_launch_search(bool self, bool excl, int n, int nq, const float* queries, const KnnTemp& t, int nb1, int nb2,
+                              int k_out, long long* idx_out, float* dist_out, float* mean_out, cudaStream_t s)
 {
     const int blocks = (nq + 127) / 128;
-    if (self) knn_search_kernel<K, true><<<blocks, 128, 0, s>>>(nq, queries, t.grid, t.cell_range, t.sorted_pts, k_out, idx_out, dist_out, mean_out);
-    else knn_search_kernel<K, false><<<blocks, 128, 0, s>>>(nq, queries, t.grid, t.cell_range, t.sorted_pts, k_out, idx_out, dist_out, mean_out);
+    if (self && excl)
+        knn_search_kernel<K, true, true><<<blocks, 128, 0, s>>>(n, nq, queries, t.sorted_pts, t.box1, nb1, t.box2, nb2, k_out, idx_out, dist_out, mean_out);
+    else if (self)
+        knn_search_kernel<K, true, false><<<blocks, 128, 0, s>>>(n, nq, queries, t.sorted_pts, t.box1, nb1, t.box2, nb2, k_out, idx_out, dist_out, mean_out);
+    else
+        knn_search_kernel<K, false, false><<<blocks, 128, 0, s>>>(n, nq, queries, t.sorted_pts, t.box1, nb1, t.box2, nb2, k_out, idx_out, dist_out, mean_out);
 }
 
 int launch_knn(int n, const float* points, int nq, const float* queries, int K, bool exclude_self, long long* idx_out,
@@ -252,30 +283,30 @@ int launch_knn(int n, const float* points, int nq, const float* queries, int K, 
 {
     KnnTemp t;
     knn_temp_layout((size_t)n, &t, (char*)temp);
+    const int nb1 = (n + KNN_L1 - 1) / KNN_L1, nb2 = (nb1 + KNN_FAN - 1) / KNN_FAN;
     knn_bbox_init_kernel<<<1, 32, 0, s>>>(t.bbox);
     SAGARS_LAUNCH_CHECK(s, false);
     knn_bbox_kernel<<<min((n + 255) / 256, 148 * 8), 256, 0, s>>>(n, points, t.bbox);
     SAGARS_LAUNCH_CHECK(s, false);
-    knn_grid_setup_kernel<<<1, 1, 0, s>>>(n, t.bbox, t.grid);
-    SAGARS_LAUNCH_CHECK(s, false);
-    // cell ids < n: sort bits [0, bits(n))
-    int bits = 1;
-    while (bits < 32 && (1ll << bits) < (long long)n + 1) bits++;
+    constexpr int bits = 30;
     const bool start_alt = (sort_num_passes(bits) & 1) != 0;
-    knn_cell_keys_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, points, t.grid, start_alt ? t.keys_b : t.keys_a, start_alt ? t.vals_b : t.vals_a);
+    knn_morton_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, points, t.bbox, start_alt ? t.keys_b : t.keys_a, start_alt ? t.vals_b : t.vals_a);
     SAGARS_LAUNCH_CHECK(s, false);
     bool in_a = true;
     int rc = launch_sort_pairs(nullptr, n, bits, t.keys_a, t.vals_a, t.keys_b, t.vals_b, t.sort_temp, sort_temp_bytes((size_t)n),
                                false, &in_a, s, false);
     if (rc) return rc;
-    SAGARS_CUDA(cudaMemsetAsync(t.cell_range, 0, (size_t)n * sizeof(uint2), s));
-    knn_ranges_gather_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, t.keys_a, t.vals_a, points, t.cell_range, t.sorted_pts);
+    knn_gather_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, t.vals_a, points, t.sorted_pts);
     SAGARS_LAUNCH_CHECK(s, false);
-    const float* qp = queries ? queries : points;
-    if (K <= 4) knn_launch_search<4>(exclude_self, nq, qp, t, K, idx_out, dist_out, mean_out, s);
-    else if (K <= 8) knn_launch_search<8>(exclude_self, nq, qp, t, K, idx_out, dist_out, mean_out, s);
-    else if (K <= 16) knn_launch_search<16>(exclude_self, nq, qp, t, K, idx_out, dist_out, mean_out, s);
-    else knn_launch_search<32>(exclude_self, nq, qp, t, K, idx_out, dist_out, mean_out, s);
+    knn_box1_kernel<<<(nb1 * 32 + 255) / 256, 256, 0, s>>>(n, t.sorted_pts, t.box1, nb1);
+    SAGARS_LAUNCH_CHECK(s, false);
+    knn_box2_kernel<<<(nb2 + 127) / 128, 128, 0, s>>>(t.box1, nb1, t.box2, nb2);
+    SAGARS_LAUNCH_CHECK(s, false);
+    const bool self = queries == nullptr;
+    if (K <= 4) knn_launch_search<4>(self, exclude_self, n, nq, queries, t, nb1, nb2, K, idx_out, dist_out, mean_out, s);
+    else if (K <= 8) knn_launch_search<8>(self, exclude_self, n, nq, queries, t, nb1, nb2, K, idx_out, dist_out, mean_out, s);
+    else if (K <= 16) knn_launch_search<16>(self, exclude_self, n, nq, queries, t, nb1, nb2, K, idx_out, dist_out, mean_out, s);
+    else knn_launch_search<32>(self, exclude_self, n, nq, queries, t, nb1, nb2, K, idx_out, dist_out, mean_out, s);
     SAGARS_LAUNCH_CHECK(s, false);
     return SAGARS_OK;
 }
