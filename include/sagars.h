@@ -244,6 +244,21 @@ SAGARS_API int sagars_knn(int32_t device, int32_t num_points, const float* point
                           int32_t num_queries, const float* queries /* [Q,3] or NULL */, int32_t K, int32_t exclude_self,
                           int64_t* idx_out, float* dist2_out, float* mean_dist2_out, void* temp, void* stream);
 
+/* Fused feature smoothing in front of the rasterizer:
+ *     out_i = mean_k( F[idx[i,k]] / max(||F[idx[i,k]]||, 1e-12) ),   optionally  out_i /= (||out_i|| + 1e-9)
+ * Replaces the tensor expression of scene/gaussian_model_ff.py:338-364 (`F.normalize(...)[select_idx, :].mean(dim=1)`)
+ * and gaussian_renderer/__init__.py:362-363 (`colors_precomp / (colors_precomp.norm(dim=1, keepdim=True) + 1e-9)`)
+ * and their autograd backward (a [P,Ks,C] scatter-add).  features [P,C] fp32, nbr_idx [P,Ks] int64 (entries in [0,P)),
+ * out [P,C]; (when normalize_out) mean_norm [P] is an output of the forward that the backward needs.
+ * The backward accumulates through dL_dn_scratch [P,C] (zeroed by the library) and writes dL_dfeatures [P,C] in full. */
+SAGARS_API int sagars_smooth_forward(int32_t device, int32_t P, int32_t C, int32_t Ks, const float* features,
+                                     const int64_t* nbr_idx, int32_t normalize_out, float* out,
+                                     float* mean_norm, void* stream);
+SAGARS_API int sagars_smooth_backward(int32_t device, int32_t P, int32_t C, int32_t Ks, const float* features,
+                                      const int64_t* nbr_idx, int32_t normalize_out,
+                                      const float* mean_norm, const float* out, const float* dL_dout,
+                                      float* dL_dn_scratch, float* dL_dfeatures, void* stream);
+
 /* number of kernels launched by this library (process-wide) since the last reset
  * (bench.py reports it as `gpu_launches`). */
 SAGARS_API int64_t sagars_launch_count(void);

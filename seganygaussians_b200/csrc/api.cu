@@ -498,4 +498,36 @@ int sagars_knn(int32_t device, int32_t num_points, const float* points, int32_t 
                       mean_dist2_out, temp, (cudaStream_t)stream);
 }
 
+int sagars_smooth_forward(int32_t device, int32_t P, int32_t C, int32_t Ks, const float* features, const int64_t* nbr_idx,
+                          int32_t normalize_out, float* out, float* mean_norm, void* stream)
+{
+    g_err[0] = 0;
+    if (P < 0 || C < 1 || C > SAGARS_MAX_CHANNELS || Ks < 1 ||
+        (P > 0 && (!features || !nbr_idx || !out || (normalize_out && !mean_norm)))) {
+        set_error("sagars_smooth_forward: bad argument (1 <= C <= %d, Ks >= 1)", SAGARS_MAX_CHANNELS);
+        return SAGARS_EINVAL;
+    }
+    if (P == 0) return SAGARS_OK;
+    SAGARS_CUDA(cudaSetDevice(device));
+    return launch_smooth_forward(P, C, Ks, features, (const long long*)nbr_idx, normalize_out, out, mean_norm,
+                                 (cudaStream_t)stream);
+}
+
+int sagars_smooth_backward(int32_t device, int32_t P, int32_t C, int32_t Ks, const float* features, const int64_t* nbr_idx,
+                           int32_t normalize_out, const float* mean_norm, const float* out,
+                           const float* dL_dout, float* dL_dn_scratch, float* dL_dfeatures, void* stream)
+{
+    g_err[0] = 0;
+    if (P < 0 || C < 1 || C > SAGARS_MAX_CHANNELS || Ks < 1 ||
+        (P > 0 && (!features || !nbr_idx || !dL_dout || !dL_dn_scratch || !dL_dfeatures ||
+                   (normalize_out && (!mean_norm || !out))))) {
+        set_error("sagars_smooth_backward: bad argument");
+        return SAGARS_EINVAL;
+    }
+    if (P == 0) return SAGARS_OK;
+    SAGARS_CUDA(cudaSetDevice(device));
+    return launch_smooth_backward(P, C, Ks, features, (const long long*)nbr_idx, normalize_out, mean_norm, out,
+                                  dL_dout, dL_dn_scratch, dL_dfeatures, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -194,6 +194,11 @@ int launch_sort_pairs(const uint32_t* n_dev, int cap, int end_bit, uint64_t* key
                       cudaStream_t s, bool debug);
 int sort_num_passes(int end_bit);
 int launch_tile_ranges(const uint32_t* n_dev, int cap, int num_tiles, const uint64_t* keys, uint2* ranges, cudaStream_t s, bool debug);
+int launch_smooth_forward(int P, int C, int Ks, const float* F, const long long* idx, int normalize_out, float* out,
+                          float* mean_norm, cudaStream_t s);
+int launch_smooth_backward(int P, int C, int Ks, const float* F, const long long* idx, int normalize_out,
+                           const float* mean_norm, const float* out, const float* dL_dout, float* dL_dn, float* dL_dF,
+                           cudaStream_t s);
 size_t knn_temp_bytes(size_t n);
 int launch_knn(int n, const float* points, int nq, const float* queries, int K, bool exclude_self, long long* idx_out,
                float* dist_out, float* mean_out, void* temp, cudaStream_t s);

@@ -139,6 +139,27 @@ def render_with_depth(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0
             "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii}
 
 
+def _fused_traditional_smoothing(pc, K, dropout, normalize_output):
+    """``pc.get_smoothed_point_features(K, dropout)`` (+ the renderer's renormalisation) as ONE fused op
+    (``seganygaussians_b200.smoothing``).  Same neighbour map, same ``torch.randperm`` draw as the reference
+    (scene/gaussian_model_ff.py:338-364), so the selected neighbours are identical.  Returns None when the model does
+    not look like the reference's FeatureGaussianModel (the caller then uses the model's own method)."""
+    if K <= 1 or not hasattr(pc, "feature_smooth_map") or not hasattr(pc, "_point_features"):
+        return None
+    if not (0 < dropout < 1) or int(K * dropout) < 1 or not pc._point_features.is_cuda:
+        return None
+    from seganygaussians_b200.smoothing import smooth_point_features
+    with torch.no_grad():
+        if pc.feature_smooth_map is None or pc.feature_smooth_map["K"] != K:
+            import pytorch3d.ops
+            xyz = pc.get_xyz
+            nearest_k_idx = pytorch3d.ops.knn_points(xyz.unsqueeze(0), xyz.unsqueeze(0), K=K).idx.squeeze()
+            pc.feature_smooth_map = {"K": K, "m": nearest_k_idx}
+    select_point = torch.randperm(K)[: int(K * dropout)]
+    select_idx = pc.feature_smooth_map["m"][:, select_point]
+    return smooth_point_features(pc._point_features, select_idx, normalize_output)
+
+
 def render_contrastive_feature(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, norm_point_features=False,
                                smooth_type=None, smooth_weights=None, smooth_K=16):
     """K-dim affinity-feature render at the camera's feature resolution (reference
@@ -154,7 +175,11 @@ def render_contrastive_feature(viewpoint_camera, pc, pipe, bg_color, scaling_mod
     elif smooth_type == 'multi_res':
         colors_precomp = pc.get_multi_resolution_smoothed_point_features(smooth_weights=smooth_weights)
     elif smooth_type == 'traditional':
-        colors_precomp = pc.get_smoothed_point_features(K=smooth_K, dropout=0.5)
+        fused = _fused_traditional_smoothing(pc, smooth_K, 0.5, norm_point_features)
+        if fused is not None:
+            colors_precomp, norm_point_features = fused, False      # the fused op already renormalised
+        else:
+            colors_precomp = pc.get_smoothed_point_features(K=smooth_K, dropout=0.5)
     if norm_point_features:
         colors_precomp = colors_precomp / (colors_precomp.norm(dim=1, keepdim=True) + 1e-9)
     rendered_image, radii = rasterizer(means3D=pc.get_xyz, means2D=screenspace_points, shs=None,
