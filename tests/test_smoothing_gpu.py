@@ -68,3 +68,57 @@ def test_drop_in_renderer_uses_the_same_neighbours_as_the_reference_method():
     sel = torch.randperm(K)[: int(K * 0.5)]
     ref = reference_expression(pc._point_features, pc.feature_smooth_map["m"][:, sel], True)
     assert torch.allclose(fused, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_training_step_front_end_end_to_end():
+    """What one SAGA training iteration asks of the drop-in (`train_contrastive_feature.py:228`):
+    `render_contrastive_feature(cam, feature_gaussians, pipe, bg, norm_point_features=True, smooth_type='traditional',
+    smooth_K=16)` on a model without a neighbour map yet -> KNN map through the pytorch3d stand-in, fused smoothing,
+    K=32 rasterization, gradients back to `_point_features`.  Checked against the same pipeline assembled by hand from
+    the reference's tensor expression and a brute-force neighbour map."""
+    import importlib
+    import math
+    import numpy as np
+    import seganygaussians_b200 as S
+    from seganygaussians_b200 import synthetic
+    from seganygaussians_b200.smoothing import reference_expression
+    from oracle import knn_oracle
+    S.activate()
+    gr = importlib.import_module("gaussian_renderer")
+    assert "seganygaussians_b200" in gr.__file__
+    P, H, W, K = 6000, 96, 128, 32
+    sc = synthetic.scene(P, H, W, K)
+    g, c = sc.gauss, sc.cam
+    dev = torch.device("cuda")
+    feats = (torch.randn(P, K, generator=torch.Generator().manual_seed(4))).to(dev).requires_grad_(True)
+    pc = SimpleNamespace(get_xyz=g.means3D.to(dev), get_opacity=g.opacities.to(dev), get_scaling=g.scales.to(dev),
+                         get_rotation=g.rotations.to(dev), _point_features=feats, get_point_features=feats,
+                         feature_smooth_map=None, active_sh_degree=0)
+    cam = SimpleNamespace(FoVx=2 * math.atan(c.tanfovx), FoVy=2 * math.atan(c.tanfovy), feature_height=H, feature_width=W,
+                          world_view_transform=c.world_view_transform.to(dev), full_proj_transform=c.full_proj_transform.to(dev),
+                          camera_center=c.camera_center.to(dev))
+    pipe = SimpleNamespace(debug=False, compute_cov3D_python=False, convert_SHs_python=False)
+    bg = torch.zeros(K, device=dev)
+    dL = sc.dL_dout.to(dev)
+
+    torch.manual_seed(77)
+    out = gr.render_contrastive_feature(cam, pc, pipe, bg, norm_point_features=True, smooth_type="traditional", smooth_K=16)
+    (out["render"] * dL).sum().backward()
+    got_img, got_grad = out["render"].detach().clone(), feats.grad.detach().clone()
+    assert pc.feature_smooth_map["K"] == 16 and pc.feature_smooth_map["m"].shape == (P, 16)
+    # the neighbour map is the exact 16-NN map (self first)
+    oi, od = knn_oracle.knn_bruteforce(g.means3D.numpy(), None, K=16)
+    m = pc.feature_smooth_map["m"].cpu().numpy()
+    d_m = ((g.means3D.numpy()[m] - g.means3D.numpy()[:, None, :]) ** 2).sum(-1)
+    assert np.allclose(d_m, od, rtol=1e-5, atol=1e-10) and np.array_equal(m[:, 0], np.arange(P))
+
+    feats.grad = None
+    torch.manual_seed(77)
+    sel = torch.randperm(16)[:8]
+    colors = reference_expression(feats, pc.feature_smooth_map["m"][:, sel], True)
+    rast = gr.GaussianRasterizerContrastiveF(gr._settings(cam, pc, pipe, bg, 1.0, H, W))
+    img, _ = rast(means3D=pc.get_xyz, means2D=torch.zeros_like(pc.get_xyz, requires_grad=True), shs=None, colors_precomp=colors,
+                  opacities=pc.get_opacity, scales=pc.get_scaling, rotations=pc.get_rotation, cov3D_precomp=None)
+    (img * dL).sum().backward()
+    assert torch.allclose(got_img, img, rtol=1e-4, atol=2e-5 * float(img.abs().max()))
+    assert torch.allclose(got_grad, feats.grad, rtol=1e-3, atol=2e-5 * float(feats.grad.abs().max()))
