@@ -120,5 +120,6 @@ def test_training_step_front_end_end_to_end():
     img, _ = rast(means3D=pc.get_xyz, means2D=torch.zeros_like(pc.get_xyz, requires_grad=True), shs=None, colors_precomp=colors,
                   opacities=pc.get_opacity, scales=pc.get_scaling, rotations=pc.get_rotation, cov3D_precomp=None)
     (img * dL).sum().backward()
+    img = img.detach()
     assert torch.allclose(got_img, img, rtol=1e-4, atol=2e-5 * float(img.abs().max()))
     assert torch.allclose(got_grad, feats.grad, rtol=1e-3, atol=2e-5 * float(feats.grad.abs().max()))
