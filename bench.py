@@ -210,6 +210,7 @@ def main():
                                      scales=scales, rotations=rots, cov3D_precomp=None)
         last["num_rendered"] = int(color.grad_fn.num_rendered)
         last["radii"] = radii
+        last["image_state"] = color.grad_fn.saved_tensors[-1]   # opaque byte tensor; decoded after the timed region
         color.backward(dL)
         if use_dist:
             dist.all_reduce(colors.grad)
@@ -282,6 +283,17 @@ def main():
     R_inst = last["num_rendered"]
     radii_vis = int((last["radii"] > 0).sum().item())
     T_tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    # work-proportional counters: S = pair tests a tile-per-CTA traversal would make at most
+    # (256 threads x every instance of the tile); n_contrib summed = pairs up to each pixel's last contributor.
+    S_pairs = 256 * R_inst
+    pairs_to_last = None
+    if a.impl == "ours":
+        try:
+            il = _lib.image_layout(W, H)
+            raw = last["image_state"][il.n_contrib: il.n_contrib + 4 * H * W]
+            pairs_to_last = int(raw.view(torch.int32).sum(dtype=torch.int64).item())
+        except Exception:
+            pairs_to_last = None
     line = {
         "metric": "fwd+bwd Gaussians*pixels/s @K=32", "value": value, "unit": "Gaussian*pixel/s",
         "n_gpus": world if (use_dist or a.impl != "ours") else a.gpus, "steps": a.steps, "warmup": max(a.warmup, 3),
@@ -294,7 +306,7 @@ def main():
                    "P_visible": radii_vis, "R_instances": R_inst,
                    "kernels": {"forward": "mma.sync warp kernel" if a.fwd_kernel == "default" else "tcgen05 tile kernel",
                                "backward": "mma.sync warp kernel" if a.bwd_kernel == "default" else "mma.sync tile kernel"},
-                   "S_pair_tests": None},
+                   "S_pair_tests_upper_bound": S_pairs, "pairs_up_to_last_contributor": pairs_to_last},
         "e2e": {"value": e2e_value, "unit": "Gaussian*pixel/s", "ms_per_step": ms_e2e / a.steps,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
                 "note": "camera from pinned host memory each step; loss scalar + num_rendered read back"},
@@ -328,6 +340,7 @@ def main():
         line["gpu_launches"] = None
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(sc, K)
+        line["cpu_autograd_c1"] = cpu_autograd_c1()
     print(json.dumps(line))
     if use_dist:
         dist.destroy_process_group()
@@ -348,6 +361,23 @@ def cpu_baseline(sc, K, max_seconds=40.0):
     return {"value": float(P) * H * W / dt, "unit": "Gaussian*pixel/s", "cores": nthreads, "kind": "port",
             "seconds": dt,
             "sample": f"1 fwd+bwd step of the full workload (P={P}, {H}x{W}, K={K}) with the C oracle port, {nthreads} OpenMP threads"}
+
+
+def cpu_autograd_c1():
+    """BASELINE.json configs[0]: SYN(10k, 256x256, K=3) forward + backward on the host through the PyTorch-autograd
+    restatement (oracle/autograd_oracle.py, float64, one thread).  Reported beside the C port; not the headline."""
+    try:
+        from oracle import autograd_oracle
+        from seganygaussians_b200 import synthetic
+        P1, H1, W1, K1 = 10_000, 256, 256, 3
+        sc1 = synthetic.scene(P1, H1, W1, K1)
+        t0 = time.time()
+        out = autograd_oracle.run_scene(sc1, K1)
+        dt = time.time() - t0
+        return {"value": float(P1) * H1 * W1 / dt, "unit": "Gaussian*pixel/s", "cores": 1, "kind": "port", "seconds": dt,
+                "sample": f"1 fwd+bwd of SYN({P1}, {H1}x{W1}, K={K1}) (BASELINE configs[0]), torch.autograd float64, R={out.num_rendered}"}
+    except Exception as e:   # pragma: no cover
+        return {"value": None, "error": repr(e)}
 
 
 def reference_cpu_arm(a, wl, sc):
