@@ -210,7 +210,6 @@ def main():
                                      scales=scales, rotations=rots, cov3D_precomp=None)
         last["num_rendered"] = int(color.grad_fn.num_rendered)
         last["radii"] = radii
-        last["image_state"] = color.grad_fn.saved_tensors[-1]   # opaque byte tensor; decoded after the timed region
         color.backward(dL)
         if use_dist:
             dist.all_reduce(colors.grad)
@@ -288,9 +287,12 @@ def main():
     S_pairs = 256 * R_inst
     pairs_to_last = None
     if a.impl == "ours":
-        try:
+        try:   # one extra UNTIMED forward: n_contrib lives in the call's opaque image-state buffer
+            color_x, _ = rast_resident(means3D=means3D, means2D=means2D, opacities=opac, shs=None, colors_precomp=colors,
+                                       scales=scales, rotations=rots, cov3D_precomp=None)
+            img_state = color_x.grad_fn.saved_tensors[-1]
             il = _lib.image_layout(W, H)
-            raw = last["image_state"][il.n_contrib: il.n_contrib + 4 * H * W]
+            raw = img_state[il.n_contrib: il.n_contrib + 4 * H * W]
             pairs_to_last = int(raw.view(torch.int32).sum(dtype=torch.int64).item())
         except Exception:
             pairs_to_last = None
