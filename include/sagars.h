@@ -74,6 +74,10 @@ enum {
 #define SAGARS_FLAG_FWD_WARP_ANY 256u /* forward: the warp-per-block tensor-core kernel for every colour-only channel count
                                         (default: only C = 32; other counts use the fp32 SIMT kernel, bit-exact colours)  */
 
+#define SAGARS_FLAG_STAGE_TMA 512u   /* tile-per-CTA fp32 forward (render_forward.cu): gather the per-instance records / feature rows
+                                        with bulk asynchronous copies (cp.async.bulk, TMA unit) completing on mbarriers instead of
+                                        16-byte cp.async pieces.  Identical results; opt-in until measured   */
+
 /* Allocator callback: return a device pointer to at least `bytes` bytes (256-B aligned), or NULL.
  * Replaces: std::function<char*(size_t)> geometryBuffer / binningBuffer / imageBuffer
  *           (CF cuda_rasterizer/rasterizer.h:33-35). */

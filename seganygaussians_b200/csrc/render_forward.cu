@@ -14,7 +14,11 @@
 //     256-instance batch);
 //   * a (warp, splat) pair in which no pixel can pass the reference's tests (power <= 0 and a conservative
 //     per-splat lower bound on power that implies alpha >= 1/255) is rejected with one warp vote, before expf;
-//   * C is a run-time value (<= 64), dispatched onto float4-group templates.
+//   * C is a run-time value (<= 64), dispatched onto float4-group templates;
+//   * SAGARS_FLAG_STAGE_TMA selects a second staging engine for the same kernel body: the 32-byte records and
+//     (K % 4 == 0) the K*4-byte feature rows of a batch are gathered by bulk asynchronous copies (cp.async.bulk, the
+//     TMA unit's non-tensor form: ONE instruction per row, issued by warp 0, no per-thread 16-byte pieces) that complete
+//     on an mbarrier per pipeline stage; consumers wait on the barrier's phase instead of cp.async.wait_all.
 // The per-pixel arithmetic (power, alpha, the 1/255 and 1e-4 tests, the order of accumulation)
 // is kept operation for operation so that n_contrib / final_T / colours match the reference.
 #include "common.cuh"
@@ -34,13 +38,60 @@ struct FwdSmem {
     float depthv[2][FWD_BATCH];         // DEPTH variant: per-instance view depth
 };
 
+template <int NQ>
+struct FwdSmemTma : FwdSmem<NQ> {
+    uint64_t bar[2];                    // one mbarrier per pipeline stage (bulk-copy staging only)
+};
+template <int NQ, bool TMA>
+struct FwdSmemSel { using type = FwdSmem<NQ>; };
+template <int NQ>
+struct FwdSmemSel<NQ, true> { using type = FwdSmemTma<NQ>; };
+
+// bulk-copy staging of one batch: warp 0 announces the bytes of the batch on the stage's mbarrier and gathers the
+// rows, one cp.async.bulk per row (record: 32 B; feature row: K*4 B when K % 4 == 0)
+template <int NQ, bool VEC, bool COLOR>
+__device__ __forceinline__ void fwd_issue_batch_bulk(FwdSmemTma<NQ>& sm, int stage, int idbuf, int cnt, int K,
+                                                     const float* __restrict__ geo, const float* __restrict__ features)
+{
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    const uint32_t row_bytes = (VEC && COLOR) ? (uint32_t)K * 4u : 0u;
+    uint64_t* bar = &sm.bar[stage];
+    if (lane == 0) mbarrier_arrive_expect_tx(bar, (uint32_t)cnt * (32u + row_bytes));
+    __syncwarp();
+    for (int j = lane; j < cnt; j += 32) {
+        const uint32_t id = sm.ids[idbuf][j];
+        bulk_copy_g2s(&sm.geo[stage][j][0], geo + 8 * (size_t)id, 32u, bar);
+        if (VEC && COLOR) bulk_copy_g2s(&sm.feat[stage][j][0], features + (size_t)id * K, row_bytes, bar);
+    }
+}
+
 // issue the asynchronous copies of one batch (ids already in smem)
-template <int NQ, bool VEC, bool MD, bool COLOR>
-__device__ __forceinline__ void fwd_issue_batch(FwdSmem<NQ>& sm, int stage, int idbuf, int cnt, int K,
+template <int NQ, bool VEC, bool MD, bool COLOR, bool TMA = false>
+__device__ __forceinline__ void fwd_issue_batch(typename FwdSmemSel<NQ, TMA>::type& sm, int stage, int idbuf, int cnt, int K,
                                                 const float* __restrict__ geo, const float* __restrict__ features,
                                                 const float* __restrict__ mask, const float* __restrict__ depths)
 {
     const int tid = threadIdx.x;
+    if constexpr (TMA) {
+        fwd_issue_batch_bulk<NQ, VEC, COLOR>(sm, stage, idbuf, cnt, K, geo, features);
+        if (MD) {
+            if (tid < cnt) {
+                const uint32_t id = sm.ids[idbuf][tid];
+                sm.maskv[stage][tid] = mask[id];
+                sm.depthv[stage][tid] = depths[id];
+            }
+        }
+        if (COLOR && !VEC) {
+            float* f = reinterpret_cast<float*>(&sm.feat[stage][0][0]);
+            for (int c = tid; c < cnt * K; c += TILE_PIX) {
+                const int j = c / K, k = c - j * K;
+                const uint32_t id = sm.ids[idbuf][j];
+                f[j * (4 * NQ) + k] = features[(size_t)id * K + k];
+            }
+        }
+        return;
+    }
     // geometry records: 2 x 16 B per instance
     for (int c = tid; c < cnt * 2; c += TILE_PIX) {
         const int j = c >> 1, h = c & 1;
@@ -83,17 +134,18 @@ __device__ __forceinline__ void fwd_pad_batch(FwdSmem<NQ>& sm, int stage, int cn
     }
 }
 
-template <int NQ, bool VEC, bool MD, bool COLOR>
-__global__ void __launch_bounds__(TILE_PIX)
-render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                      int W, int H, int K,
-                      const float* __restrict__ geo, const float* __restrict__ features,
-                      const float* __restrict__ mask, const float* __restrict__ depths, const float* __restrict__ bg,
-                      float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
-                      float* __restrict__ out_color, float* __restrict__ out_mask, float* __restrict__ out_depth)
+template <int NQ, bool VEC, bool MD, bool COLOR, bool TMA>
+__device__ __forceinline__ void
+render_forward_body(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                    int W, int H, int K,
+                    const float* __restrict__ geo, const float* __restrict__ features,
+                    const float* __restrict__ mask, const float* __restrict__ depths, const float* __restrict__ bg,
+                    float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
+                    float* __restrict__ out_color, float* __restrict__ out_mask, float* __restrict__ out_depth)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    FwdSmem<NQ>& sm = *reinterpret_cast<FwdSmem<NQ>*>(smem_raw);
+    using Smem = typename FwdSmemSel<NQ, TMA>::type;
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_x = gridDim.x;
@@ -113,6 +165,15 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         float* f = reinterpret_cast<float*>(&sm.feat[0][0][0]);
         for (int c = tid; c < 2 * FWD_BATCH * 4 * NQ; c += TILE_PIX) f[c] = 0.f;
     }
+    if constexpr (TMA) {
+        if (tid == 0) {
+            mbarrier_init(&sm.bar[0], 1);
+            mbarrier_init(&sm.bar[1], 1);
+        }
+        // the barriers and the zero fill above (generic proxy) before the first bulk copy (async proxy) touches them;
+        // the __syncthreads of the prologue below orders every thread's fence before warp 0 issues
+        fence_proxy_async_smem();
+    }
 
     float T = 1.0f;
     uint32_t last_contributor = 0;
@@ -126,10 +187,11 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     if (nbatch > 0) {
         if (tid < min(FWD_BATCH, total)) sm.ids[0][tid] = point_list[range.x + tid];
         __syncthreads();
-        fwd_issue_batch<NQ, VEC, MD, COLOR>(sm, 0, 0, min(FWD_BATCH, total), K, geo, features, mask, depths);
-        cp_async_commit();
+        fwd_issue_batch<NQ, VEC, MD, COLOR, TMA>(sm, 0, 0, min(FWD_BATCH, total), K, geo, features, mask, depths);
+        if constexpr (!TMA) cp_async_commit();
         if (nbatch > 1 && tid < min(FWD_BATCH, total - FWD_BATCH)) sm.ids[1][tid] = point_list[range.x + FWD_BATCH + tid];
-        cp_async_wait_all();
+        if constexpr (TMA) mbarrier_wait_parity(&sm.bar[0], 0u);
+        else cp_async_wait_all();
         fwd_pad_batch<NQ>(sm, 0, min(FWD_BATCH, total));
         __syncthreads();
     }
@@ -142,9 +204,9 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 
         // (A) start the copies of batch b+1 (its ids were stored one iteration ago)
         if (b + 1 < nbatch) {
-            fwd_issue_batch<NQ, VEC, MD, COLOR>(sm, stage ^ 1, (b + 1) & 1, min(FWD_BATCH, total - (b + 1) * FWD_BATCH),
-                                         K, geo, features, mask, depths);
-            cp_async_commit();
+            fwd_issue_batch<NQ, VEC, MD, COLOR, TMA>(sm, stage ^ 1, (b + 1) & 1, min(FWD_BATCH, total - (b + 1) * FWD_BATCH),
+                                              K, geo, features, mask, depths);
+            if constexpr (!TMA) cp_async_commit();
         }
         // (B) ids of batch b+2 into a register
         uint32_t next_id = 0;
@@ -207,7 +269,12 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 
         // (D) publish ids(b+2); wait for batch b+1
         if (have_next_id) sm.ids[b & 1][tid] = next_id;
-        cp_async_wait_all();
+        if constexpr (TMA) {
+            // stage s is filled by batches b = s, s + 2, ...: its (b >> 1)-th fill completes phase parity (b >> 1) & 1
+            if (b + 1 < nbatch) mbarrier_wait_parity(&sm.bar[stage ^ 1], (uint32_t)(((b + 1) >> 1) & 1));
+        } else {
+            cp_async_wait_all();
+        }
         if (b + 1 < nbatch) fwd_pad_batch<NQ>(sm, stage ^ 1, min(FWD_BATCH, total - (b + 1) * FWD_BATCH));
         __syncthreads();
     }
@@ -228,12 +295,35 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     }
 }
 
+#define SAGARS_FWD_PARAMS                                                                                        \
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int K,                 \
+    const float* __restrict__ geo, const float* __restrict__ features, const float* __restrict__ mask,              \
+    const float* __restrict__ depths, const float* __restrict__ bg, float* __restrict__ final_T,                    \
+    uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, float* __restrict__ out_mask,                  \
+    float* __restrict__ out_depth
+#define SAGARS_FWD_ARGS ranges, point_list, W, H, K, geo, features, mask, depths, bg, final_T, n_contrib, out_color, out_mask, out_depth
+
+// cp.async (LDGSTS) staging -- the default
 template <int NQ, bool VEC, bool MD, bool COLOR>
-static int launch_fwd_t(const sagars_forward_args& a, const Dims& d, GeomView g, ImageView im,
-                        const uint32_t* point_list, const float* features, cudaStream_t s, bool debug)
+__global__ void __launch_bounds__(TILE_PIX) render_forward_kernel(SAGARS_FWD_PARAMS)
 {
-    auto kern = render_forward_kernel<NQ, VEC, MD, COLOR>;
-    const size_t smem = sizeof(FwdSmem<NQ>);
+    render_forward_body<NQ, VEC, MD, COLOR, false>(SAGARS_FWD_ARGS);
+}
+// bulk-copy (TMA unit) staging completing on mbarriers -- SAGARS_FLAG_STAGE_TMA
+template <int NQ, bool VEC, bool MD, bool COLOR>
+__global__ void __launch_bounds__(TILE_PIX) render_forward_tma_kernel(SAGARS_FWD_PARAMS)
+{
+    render_forward_body<NQ, VEC, MD, COLOR, true>(SAGARS_FWD_ARGS);
+}
+#undef SAGARS_FWD_PARAMS
+#undef SAGARS_FWD_ARGS
+
+template <int NQ, bool VEC, bool MD, bool COLOR, bool TMA>
+static int launch_fwd_tt(const sagars_forward_args& a, const Dims& d, GeomView g, ImageView im,
+                         const uint32_t* point_list, const float* features, cudaStream_t s, bool debug)
+{
+    auto kern = TMA ? render_forward_tma_kernel<NQ, VEC, MD, COLOR> : render_forward_kernel<NQ, VEC, MD, COLOR>;
+    const size_t smem = sizeof(typename FwdSmemSel<NQ, TMA>::type);
     {   // opt in to the dynamic shared-memory size once per device (not on every launch: the call takes the context lock)
         static uint64_t done_mask = 0;
         int dev = 0;
@@ -248,6 +338,14 @@ static int launch_fwd_t(const sagars_forward_args& a, const Dims& d, GeomView g,
                                       im.final_T, im.n_contrib, a.out_color, a.out_mask, a.out_depth);
     SAGARS_LAUNCH_CHECK(s, debug);
     return SAGARS_OK;
+}
+
+template <int NQ, bool VEC, bool MD, bool COLOR>
+static int launch_fwd_t(const sagars_forward_args& a, const Dims& d, GeomView g, ImageView im,
+                        const uint32_t* point_list, const float* features, cudaStream_t s, bool debug)
+{
+    if (a.flags & SAGARS_FLAG_STAGE_TMA) return launch_fwd_tt<NQ, VEC, MD, COLOR, true>(a, d, g, im, point_list, features, s, debug);
+    return launch_fwd_tt<NQ, VEC, MD, COLOR, false>(a, d, g, im, point_list, features, s, debug);
 }
 
 int launch_render_forward(const sagars_forward_args& a, const Dims& d, GeomView g, ImageView im,

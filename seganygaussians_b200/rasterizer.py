@@ -134,6 +134,8 @@ def _flags(settings: GaussianRasterizationSettings, extra: int = 0) -> int:
         f |= _lib.FLAG_FWD_WARP_ANY
     if _BACKWARD_KERNEL == "tile":
         f |= _lib.FLAG_BWD_TILE
+    if _STAGING == "tma":
+        f |= _lib.FLAG_STAGE_TMA
     return f
 
 
@@ -142,6 +144,8 @@ _USE_TENSOR_CORES = True
 _FORWARD_KERNEL = "default"    # "default": mma.sync warp kernel at K = 32, fp32 SIMT otherwise; "tile": tcgen05 tile kernel at
                                # K = 32; "warp_any": the warp kernel for every colour-only channel count
 _BACKWARD_KERNEL = "default"   # "default": one warp per 8x4 pixel block; "tile": one CTA per 16x16 tile
+_STAGING = "cp_async"          # how the tile-per-CTA fp32 forward gathers a batch into shared memory: "cp_async" (16-byte LDGSTS
+                               # pieces) or "tma" (one cp.async.bulk per row completing on an mbarrier; opt-in until measured)
 _SPECULATIVE_BINNING = True
 # (device index, P, W, H) -> largest instance count seen so far: the next forward of that shape asks for a binning
 # buffer 25 % larger than this BEFORE the count is known (include/sagars.h, `binning_capacity_hint`)
@@ -170,6 +174,15 @@ def set_blend_kernels(forward: str = "default", backward: str = "default") -> No
     if forward not in ("default", "tile", "warp_any") or backward not in ("default", "tile"):
         raise ValueError("forward in {'default', 'tile', 'warp_any'}, backward in {'default', 'tile'}")
     _FORWARD_KERNEL, _BACKWARD_KERNEL = forward, backward
+
+
+def set_staging(engine: str = "cp_async") -> None:
+    """Shared-memory staging engine of the tile-per-CTA fp32 forward (BASE / DEPTH / channel counts other than 32):
+    "cp_async" (default) or "tma" (bulk asynchronous copies on the TMA unit, ``SAGARS_FLAG_STAGE_TMA``).  Same results."""
+    global _STAGING
+    if engine not in ("cp_async", "tma"):
+        raise ValueError("engine in {'cp_async', 'tma'}")
+    _STAGING = engine
 
 
 def set_cub_sort(enabled: bool) -> None:
