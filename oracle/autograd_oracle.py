@@ -3,13 +3,15 @@
 Why a second oracle: ``oracle/sagars_oracle.c`` restates the reference's hand-derived backward kernels
 (CF cuda_rasterizer/backward.cu) line by line, so a misreading of a formula there would be reproduced faithfully.
 Here only the forward expressions are written down -- in float64, as tensor
-expressions, tile by tile -- and ``torch.autograd`` derives every gradient independently.  The two places where the
+expressions, tile by tile -- and ``torch.autograd`` derives every gradient independently.  The places where the
 reference's backward is NOT the derivative of its forward are modelled explicitly as stop-gradients:
 
   * A.14  alpha = min(0.99, o*G) is straight-through (CF backward.cu:499,540,556 use ``o * dL_dalpha`` also when the
           clamp was active); the ``power > 0``, ``alpha < 1/255`` and ``T < 1e-4`` tests are constants;
   * A.20  the field-of-view clamp of cov2D: a clamped t.x (t.y) is a constant -- no gradient to t.x and no
           d(clamp)/d(t.z) term (CF backward.cu:175-176, 262-264);
+  * A.23  dL_dscales is the gradient w.r.t. ``scale_modifier * scale`` without the factor ``scale_modifier``
+          (CF backward.cu:297-325) -- found by this oracle's first scale_modifier != 1 run, not listed in SURVEY.md;
   * DEPTH the mask output only produces dL_dmask (weights detached), the depth output produces no gradient
           (DEPTH backward.cu:516, __init__.py:126-182).
 
@@ -64,7 +66,10 @@ def _cov3d(scales: torch.Tensor, rotations: torch.Tensor, mod: float) -> torch.T
     R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
                      2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
                      2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], dim=1).reshape(-1, 3, 3)
-    M = R * (mod * scales).unsqueeze(1)            # R @ diag(s)
+    # the reference's dL_dscale is the derivative w.r.t. s = mod * scale, NOT multiplied by mod (CF backward.cu:297-325):
+    # value mod * scale, gradient as if d(s)/d(scale) = 1.  Invisible at the scale_modifier = 1 every training script uses.
+    s = scales + ((mod - 1.0) * scales).detach()
+    M = R * s.unsqueeze(1)                         # R @ diag(s)
     return M @ M.transpose(1, 2)
 
 

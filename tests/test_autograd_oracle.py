@@ -63,3 +63,63 @@ def test_straight_through_clamp_is_exercised():
     ok, lines = common.compare(a, o, verbose=False)
     assert ok, "\n".join(lines)
     assert np.abs(o.g_opacity).max() > 0
+
+
+def _direct(sc, K, *, cov=None, scale_modifier=1.0):
+    """C oracle and autograd oracle called directly (paths tests.common does not expose: cov3D_precomp, scale_modifier)."""
+    from oracle import oracle
+    g, c = sc.gauss, sc.cam
+    F64 = torch.float64
+    leaf = lambda t: t.detach().clone().to(F64).requires_grad_(True)
+    means3D, opac, colors = leaf(g.means3D), leaf(g.opacities), leaf(g.colors)
+    scales = None if cov is not None else leaf(g.scales)
+    rots = None if cov is not None else leaf(g.rotations)
+    cov_l = None if cov is None else leaf(cov)
+    fw = ag.forward(means3D=means3D, opacities=opac, bg=torch.zeros(3), viewmatrix=c.world_view_transform,
+                    projmatrix=c.full_proj_transform, campos=c.camera_center, image_height=sc.H, image_width=sc.W,
+                    tanfovx=c.tanfovx, tanfovy=c.tanfovy, scale_modifier=scale_modifier, colors_precomp=colors, scales=scales,
+                    rotations=rots, cov3D_precomp=cov_l)
+    (fw.color * sc.dL_dout[:K].to(F64)).sum().backward()
+    ofw = oracle.forward(means3D=g.means3D.numpy(), opacities=g.opacities.numpy(), bg=np.zeros(3, np.float32),
+                         viewmatrix=c.world_view_transform.numpy(), projmatrix=c.full_proj_transform.numpy(),
+                         campos=c.camera_center.numpy(), image_height=sc.H, image_width=sc.W, tanfovx=c.tanfovx, tanfovy=c.tanfovy,
+                         scale_modifier=scale_modifier, colors_precomp=g.colors.numpy(),
+                         scales=None if cov is not None else g.scales.numpy(), rotations=None if cov is not None else g.rotations.numpy(),
+                         cov3D_precomp=None if cov is None else cov.numpy(), num_channels=K)
+    obw = oracle.backward(ofw, sc.dL_dout[:K].numpy())
+    return fw, (means3D, opac, colors, scales, rots, cov_l), ofw, obw
+
+
+def _close(a, b, what):
+    r, d, s = common.float_err(a, b)
+    assert r <= 1.0, f"{what}: max|d|={d:.3e} max|ref|={s:.3e} tol-ratio={r:.3f}"
+
+
+def test_cov3d_precomp_gradient():
+    """dL_dcov3D (only observable on the cov3D_precomp path; off-diagonals carry the factor 2, A.19)."""
+    P, H, W, K = 300, 48, 64, 3
+    sc = synthetic.scene(P, H, W, K, sigma_px=3.0)
+    g = sc.gauss
+    Sg = ag._cov3d(g.scales.to(torch.float64), g.rotations.to(torch.float64), 1.0)
+    cov = torch.stack([Sg[:, 0, 0], Sg[:, 0, 1], Sg[:, 0, 2], Sg[:, 1, 1], Sg[:, 1, 2], Sg[:, 2, 2]], dim=1).to(torch.float32).contiguous()
+    fw, (means3D, opac, colors, _, _, cov_l), ofw, obw = _direct(sc, K, cov=cov)
+    assert ofw.num_rendered == fw.num_rendered and np.array_equal(ofw.point_list, fw.point_list)
+    _close(fw.color.detach().numpy(), ofw.color, "color")
+    _close(cov_l.grad.numpy(), obw.cov3D, "dL_dcov3D")
+    _close(means3D.grad.numpy(), obw.means3D, "dL_dmeans3D")
+    _close(opac.grad.numpy(), obw.opacity, "dL_dopacity")
+    assert np.abs(obw.cov3D).max() > 0 and np.abs(obw.scales).max() == 0      # no scale / rotation gradient on this path
+
+
+def test_scale_modifier():
+    """scale_modifier != 1: the reference's dL_dscales lacks the factor scale_modifier (CF backward.cu:297-325; the viewer's
+    scaling slider is the only caller with a value other than 1) -- the C oracle and the CUDA path keep that, and the autograd
+    oracle models it as a stop-gradient; dL_drotations and dL_dmeans3D are true derivatives."""
+    P, H, W, K = 300, 48, 64, 3
+    sc = synthetic.scene(P, H, W, K, sigma_px=2.0)
+    fw, (means3D, opac, colors, scales, rots, _), ofw, obw = _direct(sc, K, scale_modifier=1.7)
+    assert ofw.num_rendered == fw.num_rendered and np.array_equal(ofw.radii, fw.radii)
+    _close(fw.color.detach().numpy(), ofw.color, "color")
+    _close(scales.grad.numpy(), obw.scales, "dL_dscales")
+    _close(rots.grad.numpy(), obw.rotations, "dL_drotations")
+    _close(means3D.grad.numpy(), obw.means3D, "dL_dmeans3D")
