@@ -123,3 +123,34 @@ def test_scale_modifier():
     _close(scales.grad.numpy(), obw.scales, "dL_dscales")
     _close(rots.grad.numpy(), obw.rotations, "dL_drotations")
     _close(means3D.grad.numpy(), obw.means3D, "dL_dmeans3D")
+
+
+def test_random_sweep_cameras_shapes_and_conventions():
+    """24 seeded random configurations: camera position (also INSIDE the cloud: near-plane culls, splats thousands of pixels
+    wide), field of view, ragged image sizes, K in {3, 5, 32}, SH degrees 0-3, DEPTH variant, background, unnormalised
+    quaternions.  Integer state exact; floats within 5x the suite tolerance (the C oracle is fp32 like the reference, and a
+    splat at view depth 0.37 with a 1269-pixel radius loses four digits to cancellation in its mean gradient)."""
+    rng = np.random.RandomState(123)
+    for t in range(24):
+        P, H, W = int(rng.randint(50, 400)), int(rng.randint(17, 70)), int(rng.randint(17, 90))
+        K, cam, fovx = int(rng.choice([3, 3, 5, 32])), int(rng.randint(0, 8)), float(rng.uniform(0.5, 1.7))
+        use_sh = (K == 3) and rng.rand() < 0.5
+        deg = int(rng.randint(0, 4)) if use_sh else 0
+        depth = (K == 3) and rng.rand() < 0.4
+        sigma = float(rng.choice([1.0, 2.0, 5.0, 15.0]))
+        sc = synthetic.scene(P, H, W, K, cam=cam, sh_coeffs=16 if use_sh else 0, sigma_px=sigma, seed=t)
+        sc.cam = synthetic.make_camera(H, W, cam, fovx=fovx, radius=float(rng.uniform(2.0, 9.0)))
+        sc.gauss.rotations = (sc.gauss.rotations * torch.tensor(rng.uniform(0.6, 1.4, (P, 1)), dtype=torch.float32)).contiguous()
+        bg = torch.tensor(rng.uniform(0, 1, max(K, 3)).astype(np.float32)) if rng.rand() < 0.5 else None
+        a = ag.run_scene(sc, K, depth=depth, use_sh=use_sh, sh_degree=deg, bg=bg)
+        o = common.run_oracle(sc, K, depth=depth, use_sh=use_sh, sh_degree=deg, bg=bg)
+        tag = f"case {t}: P={P} {H}x{W} K={K} cam={cam} fovx={fovx:.2f} sh={use_sh}/{deg} depth={depth} sigma={sigma}"
+        for name in common.INT_FWD:
+            x, y = getattr(a, name, None), getattr(o, name, None)
+            if x is not None and y is not None:
+                assert np.array_equal(np.asarray(x), np.asarray(y)), (tag, name)
+        for name in common.FLOAT_FWD + common.GRADS:
+            x, y = getattr(a, name, None), getattr(o, name, None)
+            if x is not None and y is not None:
+                r, d, s = common.float_err(x, y)
+                assert r <= 5.0, f"{tag}: {name} max|d|={d:.3e} max|ref|={s:.3e} tol-ratio={r:.2f}"
