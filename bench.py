@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fwd-kernel", default="default", choices=["default", "tile"], help="developer A/B switch (rasterizer.set_blend_kernels)")
     ap.add_argument("--bwd-kernel", default="default", choices=["default", "tile"], help="developer A/B switch")
+    ap.add_argument("--binning", default="radix", choices=["radix", "tile_sort"], help="developer A/B switch (rasterizer.set_binning)")
     return ap.parse_args()
 
 
@@ -169,6 +170,7 @@ def main():
         from seganygaussians_b200 import rasterizer as R, _lib
         _lib.load()
         R.set_blend_kernels(forward=a.fwd_kernel, backward=a.bwd_kernel)
+        R.set_binning(a.binning)
         Settings, Rast = R.GaussianRasterizationSettings, R.GaussianRasterizerContrastiveF
     else:
         from tests import common
@@ -307,7 +309,8 @@ def main():
                    "l2": "inputs_exceed_l2 (features 128 MB + upstream gradient 265 MB + image 265 MB >> 126 MB L2)",
                    "P_visible": radii_vis, "R_instances": R_inst,
                    "kernels": {"forward": "mma.sync warp kernel" if a.fwd_kernel == "default" else "tcgen05 tile kernel",
-                               "backward": "mma.sync warp kernel" if a.bwd_kernel == "default" else "mma.sync tile kernel"},
+                               "backward": "mma.sync warp kernel" if a.bwd_kernel == "default" else "mma.sync tile kernel",
+                               "binning": a.binning},
                    "S_pair_tests_upper_bound": S_pairs, "pairs_up_to_last_contributor": pairs_to_last},
         "e2e": {"value": e2e_value, "unit": "Gaussian*pixel/s", "ms_per_step": ms_e2e / a.steps,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,

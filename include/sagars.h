@@ -78,6 +78,10 @@ enum {
                                         with bulk asynchronous copies (cp.async.bulk, TMA unit) completing on mbarriers instead of
                                         16-byte cp.async pieces.  Identical results; opt-in until measured   */
 
+#define SAGARS_FLAG_TILE_SORT 1024u  /* binning without a global sort: per-tile instance counts -> scan -> scatter -> one CTA per tile
+                                        sorts its own segment (tile_sort.cu) instead of duplicate + 6 radix passes + range
+                                        detection.  Bit-identical point_list / keys / ranges; opt-in until measured            */
+
 /* Allocator callback: return a device pointer to at least `bytes` bytes (256-B aligned), or NULL.
  * Replaces: std::function<char*(size_t)> geometryBuffer / binningBuffer / imageBuffer
  *           (CF cuda_rasterizer/rasterizer.h:33-35). */

@@ -329,27 +329,37 @@ int sagars_forward(const sagars_forward_args* a,
         if (!bin_mem) { set_error("allocator callback returned NULL"); return SAGARS_EALLOC; }
         BinningView bv = binning_view(bin_mem, (size_t)cap);
         const uint32_t* n_dev = speculative ? g.status + 1 : nullptr;   // exact layout: the host-side count is the count
-        if (cap > 0) {
-            // own sort: emit into the buffer from which an npass-long ping-pong ends in the final arrays
-            const bool start_alt = !use_cub && (sort_num_passes(end_bit) & 1);
-            uint64_t* k0 = start_alt ? bv.keys_alt : bv.point_list_keys;
-            uint32_t* v0 = start_alt ? bv.vals_alt : bv.point_list;
-            { ProfScope ps(ST_DUPLICATE, s); rc = launch_duplicate(d, g, a->radii, k0, v0, n_dev, cap, s, debug); }
+        const bool tile_sort = (a->flags & SAGARS_FLAG_TILE_SORT) != 0 && !use_cub;
+        if (cap > 0 && tile_sort) {
+            // no global sort: per-tile counts -> scan -> scatter (the tile ranges fall out), then one CTA per tile sorts its
+            // own segment (tile_sort.cu).  keys_alt holds the unsorted (depth bits, id) pairs.
+            { ProfScope ps(ST_DUPLICATE, s); rc = launch_tile_bin(d, g, a->radii, bv.keys_alt, im.ranges, n_dev, cap, s, debug); }
             if (rc) return rc;
-            bool in_a = true;
-            {
-                ProfScope ps(ST_SORT, s);
-                rc = launch_sort_pairs(n_dev, cap, end_bit, bv.point_list_keys, bv.point_list, bv.keys_alt, bv.vals_alt,
-                                       bv.sort_temp, sort_temp_bytes((size_t)cap), use_cub, &in_a, s, debug);
-            }
+            { ProfScope ps(ST_SORT, s); rc = launch_tile_sort(num_tiles, im.ranges, bv.keys_alt, bv.point_list, bv.point_list_keys, n_dev, cap, s, debug); }
             if (rc) return rc;
-            if (!in_a) {
-                SAGARS_CUDA(cudaMemcpyAsync(bv.point_list_keys, bv.keys_alt, (size_t)cap * 8, cudaMemcpyDeviceToDevice, s));
-                SAGARS_CUDA(cudaMemcpyAsync(bv.point_list, bv.vals_alt, (size_t)cap * 4, cudaMemcpyDeviceToDevice, s));
+        } else {
+            if (cap > 0) {
+                // own sort: emit into the buffer from which an npass-long ping-pong ends in the final arrays
+                const bool start_alt = !use_cub && (sort_num_passes(end_bit) & 1);
+                uint64_t* k0 = start_alt ? bv.keys_alt : bv.point_list_keys;
+                uint32_t* v0 = start_alt ? bv.vals_alt : bv.point_list;
+                { ProfScope ps(ST_DUPLICATE, s); rc = launch_duplicate(d, g, a->radii, k0, v0, n_dev, cap, s, debug); }
+                if (rc) return rc;
+                bool in_a = true;
+                {
+                    ProfScope ps(ST_SORT, s);
+                    rc = launch_sort_pairs(n_dev, cap, end_bit, bv.point_list_keys, bv.point_list, bv.keys_alt, bv.vals_alt,
+                                           bv.sort_temp, sort_temp_bytes((size_t)cap), use_cub, &in_a, s, debug);
+                }
+                if (rc) return rc;
+                if (!in_a) {
+                    SAGARS_CUDA(cudaMemcpyAsync(bv.point_list_keys, bv.keys_alt, (size_t)cap * 8, cudaMemcpyDeviceToDevice, s));
+                    SAGARS_CUDA(cudaMemcpyAsync(bv.point_list, bv.vals_alt, (size_t)cap * 4, cudaMemcpyDeviceToDevice, s));
+                }
             }
+            { ProfScope ps(ST_RANGES, s); rc = launch_tile_ranges(n_dev, cap, num_tiles, bv.point_list_keys, im.ranges, s, debug); }
+            if (rc) return rc;
         }
-        { ProfScope ps(ST_RANGES, s); rc = launch_tile_ranges(n_dev, cap, num_tiles, bv.point_list_keys, im.ranges, s, debug); }
-        if (rc) return rc;
         { ProfScope ps(ST_RENDER_FWD, s); rc = launch_render_forward(*a, d, g, im, bv.point_list, s, debug); }
         if (rc) return rc;
         if (!speculative) break;

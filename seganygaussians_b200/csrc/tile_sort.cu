@@ -1,0 +1,219 @@
+// tile_sort.cu -- tile binning WITHOUT a global sort (SAGARS_FLAG_TILE_SORT): count -> scan -> scatter -> per-tile sort.
+//
+// Same contract as binning.cu (CF cuda_rasterizer/rasterizer_impl.cu:70-138,277-317): the final
+// point_list / point_list_keys / ranges are bit-identical to a STABLE ascending sort of the emitted (tile << 32 | depth bits)
+// keys.  What is exploited: the high half of the key is the tile id, and how many instances every tile receives is known
+// before a single key is written.  So instead of 6 global radix passes over all R instances (6 x 24 B/instance of HBM
+// traffic, 18 launches):
+//   1. tile_count_kernel   : per Gaussian, point_offsets (as duplicate_kernel) and one atomic per touched tile into
+//                            ranges[tile].y                                                            (R atomics, no writes)
+//   2. tile_scan_kernel    : exclusive scan of the T tile counts (one CTA) -> ranges[tile] = (start, start)
+//   3. tile_scatter_kernel : per Gaussian, per touched tile: slot = atomicAdd(&ranges[tile].y, 1); the pair
+//                            (depth bits << 32 | Gaussian id) goes to slot.  Afterwards ranges[tile] = [start, end) -- the
+//                            reference's tile ranges fall out for free -- and every tile's segment holds its instances in
+//                            arbitrary order                                                           (8 B/instance written)
+//   4. tile_sort_*_kernel  : one CTA per tile sorts its segment by the 64-bit pair.  Within a tile every Gaussian occurs at
+//                            most once and the reference's emission order is ascending Gaussian id, so ascending
+//                            (depth bits, id) IS the stable order.  Segments of <= 1024 / <= 8192 pairs are sorted in shared
+//                            memory (8 KB / 64 KB), longer ones in place in global memory by the same network; the sorted
+//                            ids and the re-assembled keys are written once                    (8 B read + 12 B written)
+// The sort network is the normalised bitonic network (every comparator ascending: a "flip" stage with partner i ^ (k - 1),
+// then half-cleaners with partner i ^ j).  With all comparators ascending a segment of any length n sorts as if padded with
+// +inf to the next power of two: comparators whose upper index is >= n are skipped (sort_network.cuh; tests/test_tile_sort_network.py compiles
+// that header for the host and checks the schedule for every n <= 1100 and random larger n).
+#include "common.cuh"
+#include "math.cuh"
+#include "sort_network.cuh"
+
+namespace sagars {
+
+// ---- 1. point_offsets + per-tile counts --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tile_count_kernel(int P, const float* __restrict__ geo, const uint32_t* __restrict__ tiles_touched,
+                  const uint32_t* __restrict__ block_excl, const int32_t* __restrict__ radii,
+                  uint32_t* __restrict__ point_offsets, uint2* __restrict__ ranges, int tiles_x, int tiles_y)
+{
+    __shared__ uint32_t warp_tot[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int idx = blockIdx.x * 256 + tid;
+    const uint32_t n = (idx < P) ? tiles_touched[idx] : 0u;
+    uint32_t inc = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) wbase += (w < warp) ? warp_tot[w] : 0u;
+    if (idx >= P) return;
+    point_offsets[idx] = block_excl[blockIdx.x] + wbase + inc;
+    if (n == 0) return;
+    const float4 r0 = *reinterpret_cast<const float4*>(geo + 8 * (size_t)idx);
+    uint2 rmin, rmax;
+    tile_rect(make_float2(r0.x, r0.y), radii[idx], rmin, rmax, tiles_x, tiles_y);
+    for (uint32_t y = rmin.y; y < rmax.y; y++)
+        for (uint32_t x = rmin.x; x < rmax.x; x++) atomicAdd(&ranges[y * (uint32_t)tiles_x + x].y, 1u);
+}
+
+// ---- 2. exclusive scan of the tile counts: ranges[t] = (start, start) -------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(uint2* __restrict__ ranges, int num_tiles)
+{
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry_s, slab_total_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < num_tiles; base += 1024) {
+        const int i = base + tid;
+        const uint32_t v = (i < num_tiles) ? ranges[i].y : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = warp_tot[lane];
+            uint32_t winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            warp_tot[lane] = winc - w;
+            if (lane == 31) slab_total_s = winc;
+        }
+        __syncthreads();
+        const uint32_t start = carry_s + warp_tot[warp] + (inc - v);
+        if (i < num_tiles) ranges[i] = make_uint2(start, start);
+        __syncthreads();
+        if (tid == 0) carry_s += slab_total_s;
+        __syncthreads();
+    }
+}
+
+// ---- 3. scatter the (depth bits, id) pairs into their tile's segment ------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tile_scatter_kernel(int P, const float* __restrict__ geo, const float* __restrict__ depths,
+                    const uint32_t* __restrict__ tiles_touched, const int32_t* __restrict__ radii,
+                    uint2* __restrict__ ranges, uint64_t* __restrict__ pairs, int tiles_x, int tiles_y,
+                    const uint32_t* __restrict__ n_dev, int cap)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= P || tiles_touched[idx] == 0) return;
+    if (n_dev != nullptr && *n_dev > (uint32_t)cap) return;   // layout too small: nothing may be written
+    const float4 r0 = *reinterpret_cast<const float4*>(geo + 8 * (size_t)idx);
+    uint2 rmin, rmax;
+    tile_rect(make_float2(r0.x, r0.y), radii[idx], rmin, rmax, tiles_x, tiles_y);
+    const uint64_t pair = ((uint64_t)__float_as_uint(depths[idx]) << 32) | (uint64_t)(uint32_t)idx;
+    for (uint32_t y = rmin.y; y < rmax.y; y++)
+        for (uint32_t x = rmin.x; x < rmax.x; x++) {
+            const uint32_t slot = atomicAdd(&ranges[y * (uint32_t)tiles_x + x].y, 1u);
+            pairs[slot] = pair;
+        }
+}
+
+// ---- 4. per-tile sort (comparator schedule: sort_network.cuh) ----------------------------------------------------------------
+// sorts a[0, n) ascending; a may be shared or global memory of this CTA's tile.  All threads of the CTA take part.
+template <int THREADS>
+__device__ __forceinline__ void network_sort(uint64_t* a, uint32_t n)
+{
+    const uint32_t N = network_width(n);
+    for (uint32_t k = 2; k <= N; k <<= 1) {
+        network_stage(a, n, N, k, 0u, threadIdx.x, THREADS);
+        __syncthreads();
+        for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+            network_stage(a, n, N, k, j, threadIdx.x, THREADS);
+            __syncthreads();
+        }
+    }
+}
+
+// One CTA per tile; sorts tiles whose segment length n satisfies LO < n <= HI.  HI <= shared-memory capacity: staged in
+// shared memory; HI == 0: any length above LO, in place in global memory.  The LO == 0 instance also normalises empty
+// tiles to the reference's (0, 0) range.
+template <int THREADS, uint32_t LO, uint32_t HI>
+__global__ void __launch_bounds__(THREADS)
+tile_sort_kernel(uint2* __restrict__ ranges, uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list,
+                 uint64_t* __restrict__ keys, const uint32_t* __restrict__ n_dev, int cap)
+{
+    extern __shared__ __align__(16) unsigned char tsort_smem[];
+    if (n_dev != nullptr && *n_dev > (uint32_t)cap) return;
+    const uint32_t tile = blockIdx.x;
+    const uint2 rg = ranges[tile];
+    const uint32_t n = rg.y - rg.x;
+    if (LO == 0 && n == 0) {
+        if (threadIdx.x == 0) ranges[tile] = make_uint2(0u, 0u);
+        return;
+    }
+    if (n <= LO || (HI != 0 && n > HI)) return;
+    uint64_t* seg = pairs + rg.x;
+    uint64_t* a = seg;
+    if (HI != 0) {
+        a = reinterpret_cast<uint64_t*>(tsort_smem);
+        for (uint32_t i = threadIdx.x; i < n; i += THREADS) a[i] = seg[i];
+        __syncthreads();
+    }
+    network_sort<THREADS>(a, n);
+    const uint64_t hi = (uint64_t)tile << 32;
+    for (uint32_t i = threadIdx.x; i < n; i += THREADS) {
+        const uint64_t p = a[i];
+        point_list[rg.x + i] = (uint32_t)p;
+        keys[rg.x + i] = hi | (p >> 32);
+    }
+}
+
+constexpr uint32_t TSORT_SMALL = 1024;   // pairs sorted by a 256-thread CTA in 8 KB of shared memory
+constexpr uint32_t TSORT_LARGE = 8192;   // pairs sorted by a 1024-thread CTA in 64 KB of shared memory
+
+// memset(ranges) + count + scan + scatter.  `pairs` holds cap u64.
+int launch_tile_bin(const Dims& d, GeomView g, const int32_t* radii, uint64_t* pairs, uint2* ranges,
+                    const uint32_t* n_dev, int cap, cudaStream_t s, bool debug)
+{
+    const int num_tiles = d.tiles_x * d.tiles_y;
+    const int nblk = (d.P + 255) / 256;
+    SAGARS_CUDA(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), s));
+    tile_count_kernel<<<nblk, 256, 0, s>>>(d.P, g.geo, g.tiles_touched, g.block_sums, radii, g.point_offsets, ranges,
+                                           d.tiles_x, d.tiles_y);
+    SAGARS_LAUNCH_CHECK(s, debug);
+    tile_scan_kernel<<<1, 1024, 0, s>>>(ranges, num_tiles);
+    SAGARS_LAUNCH_CHECK(s, debug);
+    tile_scatter_kernel<<<nblk, 256, 0, s>>>(d.P, g.geo, g.depths, g.tiles_touched, radii, ranges, pairs, d.tiles_x, d.tiles_y,
+                                             n_dev, cap);
+    SAGARS_LAUNCH_CHECK(s, debug);
+    return SAGARS_OK;
+}
+
+int launch_tile_sort(int num_tiles, uint2* ranges, uint64_t* pairs, uint32_t* point_list, uint64_t* keys,
+                     const uint32_t* n_dev, int cap, cudaStream_t s, bool debug)
+{
+    auto small = tile_sort_kernel<256, 0u, TSORT_SMALL>;
+    auto large = tile_sort_kernel<1024, TSORT_SMALL, TSORT_LARGE>;
+    auto huge = tile_sort_kernel<1024, TSORT_LARGE, 0u>;
+    {   // opt in to 64 KB of dynamic shared memory once per device
+        static uint64_t done_mask = 0;
+        int dev = 0;
+        SAGARS_CUDA(cudaGetDevice(&dev));
+        if (!((done_mask >> (dev & 63)) & 1ull)) {
+            SAGARS_CUDA(cudaFuncSetAttribute(large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TSORT_LARGE * 8)));
+            done_mask |= 1ull << (dev & 63);
+        }
+    }
+    small<<<num_tiles, 256, TSORT_SMALL * 8, s>>>(ranges, pairs, point_list, keys, n_dev, cap);
+    SAGARS_LAUNCH_CHECK(s, debug);
+    // the two launches below find nothing to do unless a tile holds more than 1024 / 8192 instances (every CTA returns
+    // after reading its range); the host cannot know without a read-back, so they are always queued
+    large<<<num_tiles, 1024, TSORT_LARGE * 8, s>>>(ranges, pairs, point_list, keys, n_dev, cap);
+    SAGARS_LAUNCH_CHECK(s, debug);
+    huge<<<num_tiles, 1024, 0, s>>>(ranges, pairs, point_list, keys, n_dev, cap);
+    SAGARS_LAUNCH_CHECK(s, debug);
+    return SAGARS_OK;
+}
+
+}  // namespace sagars

@@ -136,6 +136,8 @@ def _flags(settings: GaussianRasterizationSettings, extra: int = 0) -> int:
         f |= _lib.FLAG_BWD_TILE
     if _STAGING == "tma":
         f |= _lib.FLAG_STAGE_TMA
+    if _BINNING == "tile_sort":
+        f |= _lib.FLAG_TILE_SORT
     return f
 
 
@@ -146,6 +148,8 @@ _FORWARD_KERNEL = "default"    # "default": mma.sync warp kernel at K = 32, fp32
 _BACKWARD_KERNEL = "default"   # "default": one warp per 8x4 pixel block; "tile": one CTA per 16x16 tile
 _STAGING = "cp_async"          # how the tile-per-CTA fp32 forward gathers a batch into shared memory: "cp_async" (16-byte LDGSTS
                                # pieces) or "tma" (one cp.async.bulk per row completing on an mbarrier; opt-in until measured)
+_BINNING = "radix"             # "radix": duplicate keys + global LSD radix sort + range detection; "tile_sort": per-tile counts ->
+                               # scan -> scatter -> one CTA per tile sorts its segment (csrc/tile_sort.cu; opt-in until measured)
 _SPECULATIVE_BINNING = True
 # (device index, P, W, H) -> largest instance count seen so far: the next forward of that shape asks for a binning
 # buffer 25 % larger than this BEFORE the count is known (include/sagars.h, `binning_capacity_hint`)
@@ -183,6 +187,15 @@ def set_staging(engine: str = "cp_async") -> None:
     if engine not in ("cp_async", "tma"):
         raise ValueError("engine in {'cp_async', 'tma'}")
     _STAGING = engine
+
+
+def set_binning(method: str = "radix") -> None:
+    """How the (Gaussian, tile) instances are ordered: "radix" (default: the library's global radix sort of tile|depth keys) or
+    "tile_sort" (``SAGARS_FLAG_TILE_SORT``: no global sort, every tile's segment is sorted by its own CTA).  Same results."""
+    global _BINNING
+    if method not in ("radix", "tile_sort"):
+        raise ValueError("method in {'radix', 'tile_sort'}")
+    _BINNING = method
 
 
 def set_cub_sort(enabled: bool) -> None:
