@@ -329,13 +329,15 @@ int sagars_forward(const sagars_forward_args* a,
         if (!bin_mem) { set_error("allocator callback returned NULL"); return SAGARS_EALLOC; }
         BinningView bv = binning_view(bin_mem, (size_t)cap);
         const uint32_t* n_dev = speculative ? g.status + 1 : nullptr;   // exact layout: the host-side count is the count
-        const bool tile_sort = (a->flags & SAGARS_FLAG_TILE_SORT) != 0 && !use_cub;
+        // the tile sort's queue of long segments lives in the radix sort's scratch (>= 1 MB); absurdly many tiles: radix path
+        const bool tile_sort = (a->flags & SAGARS_FLAG_TILE_SORT) != 0 && !use_cub &&
+                               tile_sort_queue_bytes(num_tiles) <= sort_temp_bytes((size_t)cap);
         if (cap > 0 && tile_sort) {
             // no global sort: per-tile counts -> scan -> scatter (the tile ranges fall out), then one CTA per tile sorts its
             // own segment (tile_sort.cu).  keys_alt holds the unsorted (depth bits, id) pairs.
-            { ProfScope ps(ST_DUPLICATE, s); rc = launch_tile_bin(d, g, a->radii, bv.keys_alt, im.ranges, n_dev, cap, s, debug); }
+            { ProfScope ps(ST_DUPLICATE, s); rc = launch_tile_bin(d, g, a->radii, bv.keys_alt, im.ranges, (uint32_t*)bv.sort_temp, n_dev, cap, s, debug); }
             if (rc) return rc;
-            { ProfScope ps(ST_SORT, s); rc = launch_tile_sort(num_tiles, im.ranges, bv.keys_alt, bv.point_list, bv.point_list_keys, n_dev, cap, s, debug); }
+            { ProfScope ps(ST_SORT, s); rc = launch_tile_sort(num_tiles, im.ranges, bv.keys_alt, bv.point_list, bv.point_list_keys, (uint32_t*)bv.sort_temp, n_dev, cap, s, debug); }
             if (rc) return rc;
         } else {
             if (cap > 0) {

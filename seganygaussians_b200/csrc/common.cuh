@@ -195,10 +195,11 @@ int launch_sort_pairs(const uint32_t* n_dev, int cap, int end_bit, uint64_t* key
 int sort_num_passes(int end_bit);
 int launch_tile_ranges(const uint32_t* n_dev, int cap, int num_tiles, const uint64_t* keys, uint2* ranges, cudaStream_t s, bool debug);
 // tile_sort.cu (SAGARS_FLAG_TILE_SORT): count -> scan -> scatter (launch_tile_bin), then one CTA per tile sorts its segment
-int launch_tile_bin(const Dims& d, GeomView g, const int32_t* radii, uint64_t* pairs, uint2* ranges,
+int launch_tile_bin(const Dims& d, GeomView g, const int32_t* radii, uint64_t* pairs, uint2* ranges, uint32_t* queue,
                     const uint32_t* n_dev, int cap, cudaStream_t s, bool debug);
-int launch_tile_sort(int num_tiles, uint2* ranges, uint64_t* pairs, uint32_t* point_list, uint64_t* keys,
+int launch_tile_sort(int num_tiles, uint2* ranges, uint64_t* pairs, uint32_t* point_list, uint64_t* keys, uint32_t* queue,
                      const uint32_t* n_dev, int cap, cudaStream_t s, bool debug);
+size_t tile_sort_queue_bytes(int num_tiles);   // scratch of the long-segment queue (taken from the sort scratch)
 int launch_smooth_forward(int P, int C, int Ks, const float* F, const long long* idx, int normalize_out, float* out,
                           float* mean_norm, cudaStream_t s);
 int launch_smooth_backward(int P, int C, int Ks, const float* F, const long long* idx, int normalize_out,

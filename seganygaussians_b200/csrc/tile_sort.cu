@@ -12,11 +12,12 @@
 //                            (depth bits << 32 | Gaussian id) goes to slot.  Afterwards ranges[tile] = [start, end) -- the
 //                            reference's tile ranges fall out for free -- and every tile's segment holds its instances in
 //                            arbitrary order                                                           (8 B/instance written)
-//   4. tile_sort_*_kernel  : one CTA per tile sorts its segment by the 64-bit pair.  Within a tile every Gaussian occurs at
+//   4. tile_sort_{small,big}_kernel: one CTA per tile sorts its segment by the 64-bit pair.  Within a tile every Gaussian occurs at
 //                            most once and the reference's emission order is ascending Gaussian id, so ascending
-//                            (depth bits, id) IS the stable order.  Segments of <= 1024 / <= 8192 pairs are sorted in shared
-//                            memory (8 KB / 64 KB), longer ones in place in global memory by the same network; the sorted
-//                            ids and the re-assembled keys are written once                    (8 B read + 12 B written)
+//                            (depth bits, id) IS the stable order.  Segments of <= 1024 pairs are sorted in 8 KB of shared
+//                            memory by the tile's own CTA; longer ones are queued for a small persistent grid (<= 8192 pairs:
+//                            64 KB of shared memory; longer: in place in global memory, same network); the sorted ids and
+//                            the re-assembled keys are written once                            (8 B read + 12 B written)
 // The sort network is the normalised bitonic network (every comparator ascending: a "flip" stage with partner i ^ (k - 1),
 // then half-cleaners with partner i ^ j).  With all comparators ascending a segment of any length n sorts as if padded with
 // +inf to the next power of two: comparators whose upper index is >= n are skipped (sort_network.cuh; tests/test_tile_sort_network.py compiles
@@ -60,8 +61,9 @@ tile_count_kernel(int P, const float* __restrict__ geo, const uint32_t* __restri
 
 // ---- 2. exclusive scan of the tile counts: ranges[t] = (start, start) -------------------------------------------------------
 __global__ void __launch_bounds__(1024)
-tile_scan_kernel(uint2* __restrict__ ranges, int num_tiles)
+tile_scan_kernel(uint2* __restrict__ ranges, int num_tiles, uint32_t* __restrict__ queue)
 {
+    if (threadIdx.x == 0) queue[0] = 0u;   // length of the long-segment queue the sort kernels use
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t carry_s, slab_total_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -135,45 +137,79 @@ __device__ __forceinline__ void network_sort(uint64_t* a, uint32_t n)
     }
 }
 
-// One CTA per tile; sorts tiles whose segment length n satisfies LO < n <= HI.  HI <= shared-memory capacity: staged in
-// shared memory; HI == 0: any length above LO, in place in global memory.  The LO == 0 instance also normalises empty
-// tiles to the reference's (0, 0) range.
-template <int THREADS, uint32_t LO, uint32_t HI>
-__global__ void __launch_bounds__(THREADS)
-tile_sort_kernel(uint2* __restrict__ ranges, uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list,
-                 uint64_t* __restrict__ keys, const uint32_t* __restrict__ n_dev, int cap)
+constexpr uint32_t TSORT_SMALL = 1024;   // pairs sorted by a 256-thread CTA in 8 KB of shared memory
+constexpr uint32_t TSORT_LARGE = 8192;   // pairs sorted by a 1024-thread CTA in 64 KB of shared memory
+constexpr int TSORT_BIG_CTAS = 2 * 148;  // persistent grid of the long-segment kernel (it usually finds an empty queue)
+
+template <int THREADS>
+__device__ __forceinline__ void write_sorted(const uint64_t* a, uint32_t n, uint32_t tile, uint32_t start,
+                                             uint32_t* __restrict__ point_list, uint64_t* __restrict__ keys)
 {
-    extern __shared__ __align__(16) unsigned char tsort_smem[];
+    const uint64_t hi = (uint64_t)tile << 32;
+    for (uint32_t i = threadIdx.x; i < n; i += THREADS) {
+        const uint64_t p = a[i];
+        point_list[start + i] = (uint32_t)p;
+        keys[start + i] = hi | (p >> 32);
+    }
+}
+
+// One CTA per tile.  Segments of up to TSORT_SMALL pairs are sorted here, in shared memory; empty tiles get the reference's
+// (0, 0) range; longer segments are queued for tile_sort_big_kernel (queue[0] = count, queue[1 + i] = tile id).
+__global__ void __launch_bounds__(256)
+tile_sort_small_kernel(uint2* __restrict__ ranges, const uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list,
+                       uint64_t* __restrict__ keys, uint32_t* __restrict__ queue, const uint32_t* __restrict__ n_dev, int cap)
+{
+    __shared__ uint64_t a[TSORT_SMALL];
     if (n_dev != nullptr && *n_dev > (uint32_t)cap) return;
     const uint32_t tile = blockIdx.x;
     const uint2 rg = ranges[tile];
     const uint32_t n = rg.y - rg.x;
-    if (LO == 0 && n == 0) {
+    if (n == 0) {
         if (threadIdx.x == 0) ranges[tile] = make_uint2(0u, 0u);
         return;
     }
-    if (n <= LO || (HI != 0 && n > HI)) return;
-    uint64_t* seg = pairs + rg.x;
-    uint64_t* a = seg;
-    if (HI != 0) {
-        a = reinterpret_cast<uint64_t*>(tsort_smem);
-        for (uint32_t i = threadIdx.x; i < n; i += THREADS) a[i] = seg[i];
-        __syncthreads();
+    if (n > TSORT_SMALL) {
+        if (threadIdx.x == 0) queue[1u + atomicAdd(&queue[0], 1u)] = tile;
+        return;
     }
-    network_sort<THREADS>(a, n);
-    const uint64_t hi = (uint64_t)tile << 32;
-    for (uint32_t i = threadIdx.x; i < n; i += THREADS) {
-        const uint64_t p = a[i];
-        point_list[rg.x + i] = (uint32_t)p;
-        keys[rg.x + i] = hi | (p >> 32);
+    for (uint32_t i = threadIdx.x; i < n; i += 256) a[i] = pairs[rg.x + i];
+    __syncthreads();
+    network_sort<256>(a, n);
+    write_sorted<256>(a, n, tile, rg.x, point_list, keys);
+}
+
+// Persistent CTAs over the queue of long segments: up to TSORT_LARGE pairs in 64 KB of shared memory, longer ones in place
+// in global memory (the same network; __syncthreads orders the CTA's own global accesses between stages).
+__global__ void __launch_bounds__(1024)
+tile_sort_big_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list,
+                     uint64_t* __restrict__ keys, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ n_dev, int cap)
+{
+    extern __shared__ __align__(16) unsigned char tsort_smem[];
+    uint64_t* sh = reinterpret_cast<uint64_t*>(tsort_smem);
+    if (n_dev != nullptr && *n_dev > (uint32_t)cap) return;
+    const uint32_t count = queue[0];
+    for (uint32_t q = blockIdx.x; q < count; q += gridDim.x) {
+        const uint32_t tile = queue[1u + q];
+        const uint2 rg = ranges[tile];
+        const uint32_t n = rg.y - rg.x;
+        uint64_t* seg = pairs + rg.x;
+        if (n <= TSORT_LARGE) {
+            for (uint32_t i = threadIdx.x; i < n; i += 1024) sh[i] = seg[i];
+            __syncthreads();
+            network_sort<1024>(sh, n);
+            write_sorted<1024>(sh, n, tile, rg.x, point_list, keys);
+        } else {
+            network_sort<1024>(seg, n);
+            write_sorted<1024>(seg, n, tile, rg.x, point_list, keys);
+        }
+        __syncthreads();   // the shared buffer is reused by the next queue entry
     }
 }
 
-constexpr uint32_t TSORT_SMALL = 1024;   // pairs sorted by a 256-thread CTA in 8 KB of shared memory
-constexpr uint32_t TSORT_LARGE = 8192;   // pairs sorted by a 1024-thread CTA in 64 KB of shared memory
+size_t tile_sort_queue_bytes(int num_tiles) { return ((size_t)num_tiles + 1) * sizeof(uint32_t); }
 
-// memset(ranges) + count + scan + scatter.  `pairs` holds cap u64.
-int launch_tile_bin(const Dims& d, GeomView g, const int32_t* radii, uint64_t* pairs, uint2* ranges,
+// memset(ranges) + count + scan + scatter.  `pairs` holds cap u64; `queue`: tile_sort_queue_bytes(num_tiles) bytes.
+int launch_tile_bin(const Dims& d, GeomView g, const int32_t* radii, uint64_t* pairs, uint2* ranges, uint32_t* queue,
                     const uint32_t* n_dev, int cap, cudaStream_t s, bool debug)
 {
     const int num_tiles = d.tiles_x * d.tiles_y;
@@ -182,7 +218,7 @@ int launch_tile_bin(const Dims& d, GeomView g, const int32_t* radii, uint64_t* p
     tile_count_kernel<<<nblk, 256, 0, s>>>(d.P, g.geo, g.tiles_touched, g.block_sums, radii, g.point_offsets, ranges,
                                            d.tiles_x, d.tiles_y);
     SAGARS_LAUNCH_CHECK(s, debug);
-    tile_scan_kernel<<<1, 1024, 0, s>>>(ranges, num_tiles);
+    tile_scan_kernel<<<1, 1024, 0, s>>>(ranges, num_tiles, queue);
     SAGARS_LAUNCH_CHECK(s, debug);
     tile_scatter_kernel<<<nblk, 256, 0, s>>>(d.P, g.geo, g.depths, g.tiles_touched, radii, ranges, pairs, d.tiles_x, d.tiles_y,
                                              n_dev, cap);
@@ -190,28 +226,25 @@ int launch_tile_bin(const Dims& d, GeomView g, const int32_t* radii, uint64_t* p
     return SAGARS_OK;
 }
 
-int launch_tile_sort(int num_tiles, uint2* ranges, uint64_t* pairs, uint32_t* point_list, uint64_t* keys,
+// queue[0] was zeroed by launch_tile_bin's scan kernel
+int launch_tile_sort(int num_tiles, uint2* ranges, uint64_t* pairs, uint32_t* point_list, uint64_t* keys, uint32_t* queue,
                      const uint32_t* n_dev, int cap, cudaStream_t s, bool debug)
 {
-    auto small = tile_sort_kernel<256, 0u, TSORT_SMALL>;
-    auto large = tile_sort_kernel<1024, TSORT_SMALL, TSORT_LARGE>;
-    auto huge = tile_sort_kernel<1024, TSORT_LARGE, 0u>;
     {   // opt in to 64 KB of dynamic shared memory once per device
         static uint64_t done_mask = 0;
         int dev = 0;
         SAGARS_CUDA(cudaGetDevice(&dev));
         if (!((done_mask >> (dev & 63)) & 1ull)) {
-            SAGARS_CUDA(cudaFuncSetAttribute(large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TSORT_LARGE * 8)));
+            SAGARS_CUDA(cudaFuncSetAttribute(tile_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TSORT_LARGE * 8)));
             done_mask |= 1ull << (dev & 63);
         }
     }
-    small<<<num_tiles, 256, TSORT_SMALL * 8, s>>>(ranges, pairs, point_list, keys, n_dev, cap);
+    tile_sort_small_kernel<<<num_tiles, 256, 0, s>>>(ranges, pairs, point_list, keys, queue, n_dev, cap);
     SAGARS_LAUNCH_CHECK(s, debug);
-    // the two launches below find nothing to do unless a tile holds more than 1024 / 8192 instances (every CTA returns
-    // after reading its range); the host cannot know without a read-back, so they are always queued
-    large<<<num_tiles, 1024, TSORT_LARGE * 8, s>>>(ranges, pairs, point_list, keys, n_dev, cap);
-    SAGARS_LAUNCH_CHECK(s, debug);
-    huge<<<num_tiles, 1024, 0, s>>>(ranges, pairs, point_list, keys, n_dev, cap);
+    // the host cannot know whether any tile holds more than 1024 instances without a read-back: a small persistent grid is
+    // always queued and usually finds the queue empty
+    const int grid = num_tiles < TSORT_BIG_CTAS ? num_tiles : TSORT_BIG_CTAS;
+    tile_sort_big_kernel<<<grid, 1024, TSORT_LARGE * 8, s>>>(ranges, pairs, point_list, keys, queue, n_dev, cap);
     SAGARS_LAUNCH_CHECK(s, debug);
     return SAGARS_OK;
 }
