@@ -1,0 +1,138 @@
+// A minimal CUDA *execution shim* for the host: just enough of the device-side vocabulary (vector types, thread indices,
+// barriers, warp shuffles, atomics, bit casts) to compile simple kernels with g++ and run them with one OS thread per CUDA
+// thread.  TEST INFRASTRUCTURE ONLY (tests/test_tile_sort_emulated.py); it shadows <cuda_runtime.h> for the kernel headers
+// it is used with.  Semantics: blocks run one after the other, the threads of a block concurrently (real races and real
+// atomics), __shared__ variables are function-local statics (uninitialised across blocks, like the real thing),
+// __syncthreads / full-mask warp shuffles are barriers that tolerate threads that have already left the kernel.
+#pragma once
+#include <condition_variable>
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __constant__ static
+#define __align__(n) alignas(n)
+#define SAGARS_DYNAMIC_SMEM(name) unsigned char* name = ::cuda_emu::dynamic_smem
+
+struct float2 { float x, y; };
+struct float3 { float x, y, z; };
+struct float4 { float x, y, z, w; };
+struct uint2 { unsigned x, y; };
+struct uint3 { unsigned x, y, z; };
+inline float2 make_float2(float x, float y) { return {x, y}; }
+inline float3 make_float3(float x, float y, float z) { return {x, y, z}; }
+inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }
+inline uint2 make_uint2(unsigned x, unsigned y) { return {x, y}; }
+
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned v; std::memcpy(&v, &f, 4); return v; }
+
+inline thread_local uint3 threadIdx, blockIdx;
+inline uint3 blockDim, gridDim;
+
+namespace cuda_emu {
+
+// barrier over the threads of a group that are still inside the kernel
+struct Barrier {
+    std::mutex m;
+    std::condition_variable cv;
+    int active = 0, waiting = 0;
+    uint64_t gen = 0;
+    void reset(int n) { active = n; waiting = 0; }
+    void sync()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        if (++waiting == active) { waiting = 0; gen++; cv.notify_all(); return; }
+        const uint64_t g = gen;
+        cv.wait(lk, [&] { return gen != g; });
+    }
+    void drop()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        --active;
+        if (active > 0 && waiting == active) { waiting = 0; gen++; cv.notify_all(); }
+    }
+};
+
+struct Warp {
+    Barrier bar;
+    uint64_t slot[32];
+};
+
+inline Barrier block_bar, outer_bar;
+inline std::vector<Warp>* warps = nullptr;
+inline unsigned char* dynamic_smem = nullptr;
+
+template <class T>
+inline T shfl_from(T v, int src_lane)
+{
+    static_assert(sizeof(T) <= 8, "shuffle payload");
+    Warp& w = (*warps)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    uint64_t bits = 0;
+    std::memcpy(&bits, &v, sizeof(T));
+    w.slot[lane] = bits;
+    w.bar.sync();
+    T r = v;
+    if (src_lane >= 0 && src_lane < 32) std::memcpy(&r, &w.slot[src_lane], sizeof(T));
+    w.bar.sync();
+    return r;
+}
+
+// kernel<<<grid, block, smem>>>(args...) with 1-D grid and block
+template <class K, class... A>
+void launch(unsigned grid, unsigned block, size_t smem_bytes, K kernel, A... args)
+{
+    std::vector<unsigned char> smem(smem_bytes + 16);
+    dynamic_smem = smem.data();
+    std::vector<Warp> w((block + 31) / 32);
+    warps = &w;
+    blockDim = {block, 1, 1};
+    gridDim = {grid, 1, 1};
+    outer_bar.reset((int)block);
+    auto arm = [&] {
+        block_bar.reset((int)block);
+        for (unsigned i = 0; i < w.size(); i++) w[i].bar.reset((int)std::min(32u, block - 32 * i));
+    };
+    arm();
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < block; t++) {
+        pool.emplace_back([&, t] {
+            threadIdx = {t, 0, 0};
+            for (unsigned b = 0; b < grid; b++) {
+                blockIdx = {b, 0, 0};
+                kernel(args...);
+                block_bar.drop();                  // this thread has left the kernel: later barriers do not wait for it
+                (*warps)[t >> 5].bar.drop();
+                outer_bar.sync();
+                if (t == 0) arm();
+                outer_bar.sync();
+            }
+        });
+    }
+    for (auto& th : pool) th.join();
+    warps = nullptr;
+    dynamic_smem = nullptr;
+}
+
+}  // namespace cuda_emu
+
+inline void __syncthreads() { cuda_emu::block_bar.sync(); }
+template <class T> inline T __shfl_sync(unsigned, T v, int src) { return cuda_emu::shfl_from(v, src & 31); }
+template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned delta)
+{
+    const int lane = threadIdx.x & 31;
+    return cuda_emu::shfl_from(v, lane - (int)delta >= 0 ? lane - (int)delta : lane);
+}
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
