@@ -325,16 +325,26 @@ def main():
         dom_avg_ms = dom_ms / max(dom_n, 1)
         achieved = per_stage_bytes[dom_name] / (dom_avg_ms * 1e-3) / 1e9
         traffic = None
+        inst = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(dom_name)
+                prof = json.load(open(tp))
+                traffic = prof.get(dom_name)
+                inst = prof.get("inst_executed", {}).get(dom_name)
             except Exception:
                 traffic = None
         line["roofline"] = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": per_stage_bytes[dom_name], "avg_launch_ms": dom_avg_ms,
                             "share_of_step": dom_ms / ms_total}
+        if inst is not None and clocks and clocks.get("sm_mhz"):
+            # the bound that actually holds for the blend kernels: warp instructions issued per second against the issue-slot
+            # peak at the SM clock measured during the run (instruction count from the committed ncu capture, time live)
+            peak_issue = 148 * 4 * clocks["sm_mhz"] * 1e6
+            line["roofline"]["issue"] = {"warp_inst_per_launch": inst, "achieved_per_s": inst / (dom_avg_ms * 1e-3),
+                                         "peak_per_s": peak_issue, "frac": inst / (dom_avg_ms * 1e-3) / peak_issue,
+                                         "note": "issue-bound kernel: HBM frac is low by construction (DESIGN.md section 5)"}
         line["roofline_step"] = {"algorithmic_bytes_per_step": step_bytes,
                                  "achieved": step_bytes / (ms_total / a.steps * 1e-3) / 1e9, "unit": "GB/s",
                                  "frac": step_bytes / (ms_total / a.steps * 1e-3) / 1e9 / peak}
