@@ -338,7 +338,7 @@ def main():
                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": per_stage_bytes[dom_name], "avg_launch_ms": dom_avg_ms,
                             "share_of_step": dom_ms / ms_total}
-        if inst is not None and clocks and clocks.get("sm_mhz"):
+        if inst is not None and clocks and clocks.get("sm_mhz") and dom_avg_ms > 0:
             # the bound that actually holds for the blend kernels: warp instructions issued per second against the issue-slot
             # peak at the SM clock measured during the run (instruction count from the committed ncu capture, time live)
             peak_issue = 148 * 4 * clocks["sm_mhz"] * 1e6
