@@ -27,9 +27,7 @@
 import argparse
 import json
 import os
-import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -319,7 +317,7 @@ def main():
     }
     if a.impl == "ours":
         peak, peak_src = load_peaks()
-        per_stage_bytes, step_bytes = algorithmic_bytes(radii_vis if False else P, R_inst, H * W, T_tiles, K)
+        per_stage_bytes, step_bytes = algorithmic_bytes(P, R_inst, H * W, T_tiles, K)
         dom = max(stage.items(), key=lambda kv: kv[1][0])
         dom_name, (dom_ms, dom_n) = dom
         dom_avg_ms = dom_ms / max(dom_n, 1)
