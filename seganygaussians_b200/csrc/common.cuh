@@ -101,9 +101,12 @@ inline ImageView image_view(void* base, int W, int H) {
 }
 
 // Radix sort scratch: ping-pong key/value buffers + per-block digit counts.
+#ifndef SAGARS_SORT_CONSTANTS
+#define SAGARS_SORT_CONSTANTS
 constexpr int SORT_CHUNK = 4096;          // keys per sort block
 constexpr int SORT_RADIX_BITS = 8;
 constexpr int SORT_RADIX = 1 << SORT_RADIX_BITS;
+#endif
 
 struct BinningView {
     uint32_t* point_list;        // [R] sorted values (final)

@@ -136,3 +136,31 @@ template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned delta)
     return cuda_emu::shfl_from(v, lane - (int)delta >= 0 ? lane - (int)delta : lane);
 }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+// full-mask warp votes / matches over the lanes that take part (every lane of the warp must call, as on the device)
+template <class T> inline unsigned __match_any_sync(unsigned, T v)
+{
+    cuda_emu::Warp& w = (*cuda_emu::warps)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    uint64_t bits = 0;
+    std::memcpy(&bits, &v, sizeof(T));
+    w.slot[lane] = bits;
+    w.bar.sync();
+    unsigned m = 0;
+    const unsigned lanes = blockDim.x - (threadIdx.x & ~31u) < 32u ? blockDim.x - (threadIdx.x & ~31u) : 32u;
+    for (unsigned l = 0; l < lanes; l++) m |= (w.slot[l] == bits) ? (1u << l) : 0u;
+    w.bar.sync();
+    return m;
+}
+inline unsigned __ballot_sync(unsigned, bool pred)
+{
+    cuda_emu::Warp& w = (*cuda_emu::warps)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    w.slot[lane] = pred ? 1u : 0u;
+    w.bar.sync();
+    unsigned m = 0;
+    const unsigned lanes = blockDim.x - (threadIdx.x & ~31u) < 32u ? blockDim.x - (threadIdx.x & ~31u) : 32u;
+    for (unsigned l = 0; l < lanes; l++) m |= w.slot[l] ? (1u << l) : 0u;
+    w.bar.sync();
+    return m;
+}
