@@ -12,6 +12,14 @@
 #error "libsagars carries sm_100a code only (build with -gencode arch=compute_100a,code=sm_100a)"
 #endif
 
+// Keeps two floats opaque to the optimiser (nvcc otherwise rematerialises the pixel coordinates from %ctaid / %tid inside the
+// blend kernels' hot loops).  The CPU execution shim of the tests has no such problem and no "f" register class.
+#if defined(SAGARS_CUDA_EMU)
+#define SAGARS_PIN_F2(a, b) ((void)0)
+#else
+#define SAGARS_PIN_F2(a, b) asm volatile("" : "+f"(a), "+f"(b))
+#endif
+
 namespace sagars {
 
 constexpr int TILE_X = SAGARS_TILE_X;

@@ -4,6 +4,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#if defined(SAGARS_CUDA_EMU)
+// CPU execution shim of the test suite (tests/cuda_emu/): the same entry points with the instructions' semantics restated on
+// the host -- copies land as LATE as the programming model allows, so a read before the matching wait shows up as a failure.
+#include "cp_async_emu.h"
+#else
+
 namespace sagars {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
@@ -70,3 +76,5 @@ __device__ __forceinline__ void red_add(float* addr, float a)
 }
 
 }  // namespace sagars
+
+#endif  // SAGARS_CUDA_EMU

@@ -23,6 +23,9 @@
 #define __align__(n) alignas(n)
 #define SAGARS_DYNAMIC_SMEM(name) unsigned char* name = ::cuda_emu::dynamic_smem
 
+typedef void* cudaStream_t;      // host-side declarations of the product headers only need the names
+typedef int cudaError_t;
+
 struct float2 { float x, y; };
 struct float3 { float x, y, z; };
 struct float4 { float x, y, z, w; };
@@ -71,6 +74,7 @@ struct Warp {
 };
 
 inline Barrier block_bar, outer_bar;
+inline void (*thread_exit_hook)() = nullptr;     // e.g. "outstanding asynchronous copies of this thread land now"
 inline std::vector<Warp>* warps = nullptr;
 inline unsigned char* dynamic_smem = nullptr;
 
@@ -94,8 +98,8 @@ inline T shfl_from(T v, int src_lane)
 template <class K, class... A>
 void launch(unsigned grid, unsigned block, size_t smem_bytes, K kernel, A... args)
 {
-    std::vector<unsigned char> smem(smem_bytes + 16);
-    dynamic_smem = smem.data();
+    std::vector<unsigned char> smem(smem_bytes + 32);
+    dynamic_smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem.data()) + 15u) & ~uintptr_t(15));
     std::vector<Warp> w((block + 31) / 32);
     warps = &w;
     blockDim = {block, 1, 1};
@@ -113,6 +117,7 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, K kernel, A... arg
             for (unsigned b = 0; b < grid; b++) {
                 blockIdx = {b, 0, 0};
                 kernel(args...);
+                if (thread_exit_hook) thread_exit_hook();
                 block_bar.drop();                  // this thread has left the kernel: later barriers do not wait for it
                 (*warps)[t >> 5].bar.drop();
                 outer_bar.sync();
@@ -129,6 +134,20 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, K kernel, A... arg
 }  // namespace cuda_emu
 
 inline void __syncthreads() { cuda_emu::block_bar.sync(); }
+// barrier + AND over the threads still inside the kernel.  Two alternating flags: call k uses flag k & 1 and every thread
+// clears it again after the second barrier, long before call k + 2 can set it.
+inline int __syncthreads_and(int pred)
+{
+    static unsigned char some_false[2];
+    static thread_local unsigned call = 0;
+    unsigned char& f = some_false[call++ & 1u];
+    if (!pred) __atomic_store_n(&f, 1, __ATOMIC_RELAXED);
+    cuda_emu::block_bar.sync();
+    const int r = !__atomic_load_n(&f, __ATOMIC_RELAXED);
+    cuda_emu::block_bar.sync();
+    __atomic_store_n(&f, 0, __ATOMIC_RELAXED);
+    return r;
+}
 template <class T> inline T __shfl_sync(unsigned, T v, int src) { return cuda_emu::shfl_from(v, src & 31); }
 template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned delta)
 {
@@ -164,3 +183,12 @@ inline unsigned __ballot_sync(unsigned, bool pred)
     w.bar.sync();
     return m;
 }
+inline unsigned emu_warp_lanes() { const unsigned rest = blockDim.x - (threadIdx.x & ~31u); return rest < 32u ? rest : 32u; }
+inline bool __any_sync(unsigned, bool pred) { return __ballot_sync(0xffffffffu, pred) != 0u; }
+inline bool __all_sync(unsigned, bool pred)
+{
+    const unsigned lanes = emu_warp_lanes();
+    return __ballot_sync(0xffffffffu, pred) == (lanes == 32u ? 0xffffffffu : ((1u << lanes) - 1u));
+}
+inline void __syncwarp(unsigned = 0xffffffffu) { (*cuda_emu::warps)[threadIdx.x >> 5].bar.sync(); }
+template <class T> inline T __ldg(const T* p) { return *p; }
