@@ -3,6 +3,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#if defined(SAGARS_CUDA_EMU)
+#include "mma_emu.h"   // CPU execution shim of the test suite (tests/cuda_emu/): the same two entry points on the host
+#else
+
 namespace sagars {
 
 // x = hi + lo with hi exact in tf32 (truncation) and lo = x - hi exact in fp32; the tensor core reads the top 19 bits
@@ -24,3 +28,5 @@ __device__ __forceinline__ void mma_16n8k8(float* d, uint32_t a0, uint32_t a1, u
 }
 
 }  // namespace sagars
+
+#endif  // SAGARS_CUDA_EMU

@@ -1,0 +1,371 @@
+// render_backward_warp_kernels.cuh -- the device code of render_backward_warp.cu (see there).  Free of host-side runtime calls
+// so that tests/test_warp_kernels_emulated.py can compile it for the CPU against tests/cuda_emu/.
+#pragma once
+#include "common.cuh"
+#include "cp_async.cuh"
+#include "candidate.cuh"
+#include "mma.cuh"
+
+#ifndef SAGARS_DYNAMIC_SMEM
+#define SAGARS_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+namespace sagars {
+
+
+constexpr int BW_N = 8;      // candidates per group = rows of the W / Q tiles = N of the colour product
+constexpr int BW_TAB = 40;   // candidate table: up to 7 carried over + 32 new
+
+template <int NQ>
+struct BwCfg {
+    static constexpr int NQE = NQ < 2 ? 2 : NQ;     // quads per gradient row (power of two)
+    static constexpr int ROW = 4 * NQE;             // floats per gradient row
+    static constexpr int MT = (ROW + 15) / 16;      // 16-channel m-tiles of the transposed colour product
+};
+
+template <int NQ>
+struct BwSmem {
+    float Gs[32][BwCfg<NQ>::ROW];   // gradient row of block pixel p (= lane); quad q lives at quad (q + p) % NQE
+    float rowW[BW_N][32];           // row r, pixel p at (p + 4 r) & 31; also holds the gathered feature rows during (1)
+    float rowQ[BW_N][32];           // same layout; holds S during (2)
+    float4 ctab[BW_TAB][2];         // candidate records (x, y, cx, cy | cz, opacity, accept_threshold, -), list order
+    uint32_t cid[BW_TAB];           // their Gaussian ids
+    int32_t cpos[BW_TAB];           // their positions in the tile's list
+};
+
+// NQ : float4 groups covering the gradient channels (K colour channels [+ 1 mask channel when MD])
+// VEC: K % 4 == 0 and no mask channel -> feature rows are read as float4
+template <int NQ, bool VEC, bool MD, bool COLOR>
+__global__ void __launch_bounds__(32, (NQ <= 8) ? 28 : 12)
+render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                            int W, int H, int K,
+                            const float* __restrict__ bg, const float* __restrict__ geo,
+                            const float* __restrict__ features,
+                            const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
+                            const float* __restrict__ dL_dpix, const float* __restrict__ dL_dout_mask,
+                            float* __restrict__ ggrad, float* __restrict__ dL_dcolors)
+{
+    using Cfg = BwCfg<NQ>;
+    constexpr int NQE = Cfg::NQE, ROW = Cfg::ROW, MT = Cfg::MT;
+    SAGARS_DYNAMIC_SMEM(smem_raw);
+    BwSmem<NQ>& sm = *reinterpret_cast<BwSmem<NQ>*>(smem_raw);
+
+    const int lane = threadIdx.x;
+    const int tiles_x = (int)(gridDim.x >> 1);
+    const uint32_t blk_x0 = blockIdx.x * 8, blk_y0 = blockIdx.y * 4;
+    const uint32_t px = blk_x0 + (lane & 7), py = blk_y0 + (lane >> 3);
+    const bool inside = px < (uint32_t)W && py < (uint32_t)H;
+    const uint32_t pix_id = (uint32_t)W * py + px;
+    float pixx = (float)px, pixy = (float)py;
+    SAGARS_PIN_F2(pixx, pixy);   // keep nvcc from rematerialising them in the hot loop
+    const size_t plane = (size_t)H * W;
+
+    const uint2 range = ranges[(blockIdx.y >> 2) * tiles_x + (blockIdx.x >> 1)];
+    const int total = (int)(range.y - range.x);
+    if (total <= 0) return;   // empty tile
+
+    const float T_final = inside ? final_Ts[pix_id] : 0.f;
+    const int my_n = inside ? (int)n_contrib[pix_id] : 0;
+    int blk_n = my_n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) blk_n = max(blk_n, __shfl_xor_sync(0xffffffffu, blk_n, o));
+    const int maxc = min(blk_n, total);     // list positions [0, maxc) can contribute to this block
+    if (maxc <= 0) return;
+    const int nchunk = (maxc + 31) >> 5;
+
+    // chunk c, lane l <-> list position maxc - 1 - 32 c - l (back to front)
+    auto chunk_pos = [&](int c) { return maxc - 1 - 32 * c - lane; };
+    // first chunk's id and record, then the gradient row of this pixel: independent latency chains
+    int pos_cur = chunk_pos(0);
+    uint32_t id_cur = pos_cur >= 0 ? point_list[range.x + pos_cur] : 0u;
+
+    float bgdot = 0.f;
+    {
+        float gmask = 0.f;
+        if (MD) gmask = inside ? dL_dout_mask[pix_id] : 0.f;
+        float gr[ROW];
+#pragma unroll
+        for (int k = 0; k < ROW; k++) {
+            float x = 0.f;
+            if (COLOR && k < K) x = inside ? dL_dpix[(size_t)k * plane + pix_id] : 0.f;
+            if (MD && k == K) x = gmask;   // the mask gradient rides as channel K of the colour product
+            gr[k] = x;
+        }
+#pragma unroll
+        for (int q = 0; q < NQE; q++) {
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (COLOR && 4 * q + c < K) bgdot += bg[4 * q + c] * gr[4 * q + c];
+            *reinterpret_cast<float4*>(&sm.Gs[lane][4 * ((q + lane) & (NQE - 1))]) = make_float4(gr[4 * q], gr[4 * q + 1], gr[4 * q + 2], gr[4 * q + 3]);
+        }
+    }
+    float4 r0_cur = __ldg(reinterpret_cast<const float4*>(geo + 8 * (size_t)id_cur));
+    float4 r1_cur = __ldg(reinterpret_cast<const float4*>(geo + 8 * (size_t)id_cur + 4));
+    {   // rows past the fill level are multiplied too (their products are never used): start from finite values
+        float* w = &sm.rowW[0][0];
+        float* q = &sm.rowQ[0][0];
+#pragma unroll
+        for (int i = 0; i < BW_N; i++) { w[i * 32 + lane] = 0.f; q[i * 32 + lane] = 0.f; }
+    }
+    __syncwarp();
+
+    float T = T_final;
+    float acc_r = 0.f, last_alpha = 0.f, last_s = 0.f;
+    float* const rowW = &sm.rowW[0][0];
+    float* const rowQ = &sm.rowQ[0][0];
+
+    // mma fragment coordinates of this lane
+    const int fg = lane >> 2, ft = lane & 3;
+    const float half_W = 0.5f * (float)W, half_H = 0.5f * (float)H;   // (0.5 * W) rounded to float, as the reference
+    const float bx0 = (float)blk_x0, bx1 = bx0 + 7.f, by0 = (float)blk_y0, by1 = by0 + 3.f;   // block of pixel centres
+    const float bcx = bx0 + 3.5f, bcy = by0 + 1.5f;                                            // its centre
+    const uint32_t lt = (1u << lane) - 1u;
+
+    // one group: candidates in table slots [gs, gs + m), m <= 8
+    auto process_group = [&](int gs, int m) {
+        // ---- (1) S (32 pixels x 8) = G (32 x C) * F^T (C x 8): feature rows gathered into the W tile's storage
+        //          (row i, channel c at (c + 4 i) & 31), S written into the Q tile's storage in the Q layout ----
+        if (COLOR) {
+            float sacc[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) sacc[mt][0] = sacc[mt][1] = sacc[mt][2] = sacc[mt][3] = 0.f;
+            constexpr int QR = (ROW < 32 ? ROW : 32) / 4;      // feature quads per row and channel block
+#pragma unroll 1
+            for (int cb = 0; cb < ROW; cb += 32) {
+                if (cb > 0) __syncwarp();
+                for (int idx = lane; idx < BW_N * QR; idx += 32) {
+                    const int r = idx / QR, qd = idx - r * QR;
+                    const uint32_t id = sm.cid[gs + min(r, m - 1)];
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int c0 = cb + 4 * qd;
+                    if (VEC) {
+                        if (c0 < K) v = __ldg(reinterpret_cast<const float4*>(features + (size_t)id * K + c0));
+                    } else {
+                        const float* f = features + (size_t)id * K;
+                        if (c0 + 0 < K) v.x = __ldg(f + c0 + 0);
+                        if (c0 + 1 < K) v.y = __ldg(f + c0 + 1);
+                        if (c0 + 2 < K) v.z = __ldg(f + c0 + 2);
+                        if (c0 + 3 < K) v.w = __ldg(f + c0 + 3);
+                    }
+                    *reinterpret_cast<float4*>(rowW + r * 32 + 4 * ((qd + r) & 7)) = v;
+                }
+                __syncwarp();
+                const float* Fr = rowW + fg * 32;
+#pragma unroll
+                for (int ks = 0; ks < QR / 2; ks++) {
+                    uint32_t bh0, bl0, bh1, bl1;
+                    split_tf32(Fr[(ks * 8 + ft + 4 * fg) & 31], bh0, bl0);
+                    split_tf32(Fr[(ks * 8 + ft + 4 + 4 * fg) & 31], bh1, bl1);
+                    const int ch0 = cb + ks * 8 + ft, ch1 = ch0 + 4;
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) {
+                        const int p0 = 16 * mt + fg, p1 = p0 + 8;      // block pixels of fragment rows g and g + 8
+                        uint32_t ah[4], al[4];
+                        split_tf32(sm.Gs[p0][4 * (((ch0 >> 2) + p0) & (NQE - 1)) + (ch0 & 3)], ah[0], al[0]);
+                        split_tf32(sm.Gs[p1][4 * (((ch0 >> 2) + p1) & (NQE - 1)) + (ch0 & 3)], ah[1], al[1]);
+                        split_tf32(sm.Gs[p0][4 * (((ch1 >> 2) + p0) & (NQE - 1)) + (ch1 & 3)], ah[2], al[2]);
+                        split_tf32(sm.Gs[p1][4 * (((ch1 >> 2) + p1) & (NQE - 1)) + (ch1 & 3)], ah[3], al[3]);
+                        mma_16n8k8(sacc[mt], al[0], al[1], al[2], al[3], bh0, bh1);
+                        mma_16n8k8(sacc[mt], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+                        mma_16n8k8(sacc[mt], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+                    }
+                }
+            }
+            __syncwarp();   // the feature rows are consumed; (2) rewrites this storage row by row
+            // fragment (pixel 16 mt + fg [+8], candidates 2 ft, 2 ft + 1) -> S[i][(p + 4 i) & 31]
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) {
+                const int pa = 16 * mt + fg, pb = pa + 8;
+                rowQ[(2 * ft) * 32 + ((pa + 8 * ft) & 31)] = sacc[mt][0];
+                rowQ[(2 * ft + 1) * 32 + ((pa + 8 * ft + 4) & 31)] = sacc[mt][1];
+                rowQ[(2 * ft) * 32 + ((pb + 8 * ft) & 31)] = sacc[mt][2];
+                rowQ[(2 * ft + 1) * 32 + ((pb + 8 * ft + 4) & 31)] = sacc[mt][3];
+            }
+            __syncwarp();
+        }
+        // ---- (2) thread = pixel over the group's candidates (the reference's traversal): row i of W / Q ----
+#pragma unroll 1
+        for (int i = 0; i < m; i++) {
+            const float4 g0 = sm.ctab[gs + i][0];
+            const float4 g1 = sm.ctab[gs + i][1];
+            const float dx = g0.x - pixx, dy = g0.y - pixy;
+            const float pw = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
+            const bool cd = (sm.cpos[gs + i] < my_n) && !(pw > 0.0f) && (pw >= g1.z);
+            const int col = (lane + 4 * i) & 31;
+            float w = 0.f, q = 0.f;
+            if (cd) {
+                const float G = expf(pw);
+                const float alpha = fminf(0.99f, g1.y * G);
+                if (!(alpha < 1.0f / 255.0f)) {
+                    T = T / (1.f - alpha);
+                    const float s = COLOR ? rowQ[i * 32 + col] : 0.f;
+                    acc_r = last_alpha * last_s + (1.f - last_alpha) * acc_r;
+                    last_s = s;
+                    float dL_dalpha = (s - acc_r) * T;
+                    last_alpha = alpha;
+                    if (bgdot != 0.f) dL_dalpha += (-T_final / (1.f - alpha)) * bgdot;   // zero background: the term is exactly 0
+                    w = alpha * T;
+                    q = G * dL_dalpha;
+                }
+            }
+            rowW[i * 32 + col] = w;   // all lanes write: zero where the pixel did not blend
+            rowQ[i * 32 + col] = q;
+        }
+        __syncwarp();
+
+        // ---- (3) dL/dcolour^T = G^T W^T, moments = Q X; results -> global memory ----
+        float dc[MT][4];
+#pragma unroll
+        for (int mm = 0; mm < MT; mm++) dc[mm][0] = dc[mm][1] = dc[mm][2] = dc[mm][3] = 0.f;
+        float dm[4] = {0.f, 0.f, 0.f, 0.f};
+        {
+            // this lane's row of the tiles: column n = fg of W^T, row fg of Q; pixel p sits at column (p + 4 fg) & 31
+            const float* Wr = rowW + fg * 32;
+            const float* Qr = rowQ + fg * 32;
+            // moment basis X[p][mm] of fragment column mm = fg at block pixel (x, y): value = xa + (xb + xc * y) * y
+            const float x0 = (float)ft - 3.5f, x1 = x0 + 4.f;
+            const float xa0 = (fg == 0) ? 1.f : (fg == 1) ? x0 : (fg == 3) ? x0 * x0 : 0.f;
+            const float xa1 = (fg == 0) ? 1.f : (fg == 1) ? x1 : (fg == 3) ? x1 * x1 : 0.f;
+            const float xb0 = (fg == 2) ? 1.f : (fg == 4) ? x0 : 0.f;
+            const float xb1 = (fg == 2) ? 1.f : (fg == 4) ? x1 : 0.f;
+            const float xc = (fg == 5) ? 1.f : 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) {
+                const int c0 = (ks * 8 + ft + 4 * fg) & 31, c1 = (c0 + 4) & 31;
+                uint32_t wh0, wl0, wh1, wl1, qh0, ql0, qh1, ql1;
+                split_tf32(Wr[c0], wh0, wl0);
+                split_tf32(Wr[c1], wh1, wl1);
+                split_tf32(Qr[c0], qh0, ql0);
+                split_tf32(Qr[c1], qh1, ql1);
+                const int r0 = ks * 8 + ft, r1 = r0 + 4;     // block pixels ks*8 + ft and + 4 (same row, x and x + 4)
+                if (COLOR || MD) {
+#pragma unroll
+                    for (int mm = 0; mm < MT; mm++) {
+                        const int cl = 16 * mm + fg, chh = cl + 8;     // channels of fragment rows g and g + 8
+                        uint32_t ah[4], al[4];
+                        split_tf32(sm.Gs[r0][4 * (((cl >> 2) + r0) & (NQE - 1)) + (cl & 3)], ah[0], al[0]);
+                        split_tf32(sm.Gs[r1][4 * (((cl >> 2) + r1) & (NQE - 1)) + (cl & 3)], ah[2], al[2]);
+                        if (16 * mm + 8 < ROW) {
+                            split_tf32(sm.Gs[r0][4 * (((chh >> 2) + r0) & (NQE - 1)) + (chh & 3)], ah[1], al[1]);
+                            split_tf32(sm.Gs[r1][4 * (((chh >> 2) + r1) & (NQE - 1)) + (chh & 3)], ah[3], al[3]);
+                        } else {
+                            ah[1] = al[1] = ah[3] = al[3] = 0u;
+                        }
+                        mma_16n8k8(dc[mm], al[0], al[1], al[2], al[3], wh0, wh1);
+                        mma_16n8k8(dc[mm], ah[0], ah[1], ah[2], ah[3], wl0, wl1);
+                        mma_16n8k8(dc[mm], ah[0], ah[1], ah[2], ah[3], wh0, wh1);
+                    }
+                }
+                const float yb = (float)ks - 1.5f;
+                const float v0 = xa0 + (xb0 + xc * yb) * yb;
+                const float v1 = xa1 + (xb1 + xc * yb) * yb;
+                mma_16n8k8(dm, ql0, 0u, ql1, 0u, __float_as_uint(v0), __float_as_uint(v1));
+                mma_16n8k8(dm, qh0, 0u, qh1, 0u, __float_as_uint(v0), __float_as_uint(v1));
+            }
+        }
+        // colour product: this lane holds channels (16 mm + fg, + 8) of rows 2 ft and 2 ft + 1
+        if (COLOR || MD) {
+            const uint32_t ida = sm.cid[gs + min(2 * ft, m - 1)], idb = sm.cid[gs + min(2 * ft + 1, m - 1)];
+            const bool va = 2 * ft < m, vb = 2 * ft + 1 < m;
+            auto emit = [&](uint32_t id, int ch, float v) {
+                if (COLOR && ch < K) red_add(dL_dcolors + (size_t)id * K + ch, v);
+                else if (MD && ch == K) red_add(ggrad + (size_t)id * GG_STRIDE + 6, v);
+            };
+#pragma unroll
+            for (int mm = 0; mm < MT; mm++) {
+                const int cl = 16 * mm + fg;
+                if (va) { emit(ida, cl, dc[mm][0]); emit(ida, cl + 8, dc[mm][2]); }
+                if (vb) { emit(idb, cl, dc[mm][1]); emit(idb, cl + 8, dc[mm][3]); }
+            }
+        }
+        // moments of row fg: (m0, mx) in lane ft = 0, (my, mxx) in ft = 1, (mxy, myy) in ft = 2 of the quad
+        {
+            const int q0 = lane & ~3;
+            const float m0 = __shfl_sync(0xffffffffu, dm[0], q0);
+            const float mx = __shfl_sync(0xffffffffu, dm[1], q0);
+            const float my = __shfl_sync(0xffffffffu, dm[0], q0 + 1);
+            const float mxx = __shfl_sync(0xffffffffu, dm[1], q0 + 1);
+            const float mxy = __shfl_sync(0xffffffffu, dm[0], q0 + 2);
+            const float myy = __shfl_sync(0xffffffffu, dm[1], q0 + 2);
+            if (fg < m && ft < 3) {
+                const uint32_t id = sm.cid[gs + fg];
+                const float4 g0 = sm.ctab[gs + fg][0];
+                const float4 g1 = sm.ctab[gs + fg][1];
+                const float conx = g0.z, cony = g0.w, conz = g1.x, o = g1.y;
+                // sums over the pixels of q * (1, dx, dy, dx^2, dx dy, dy^2) with d = centre - pixel = c - x'
+                const float cx = g0.x - bcx, cy = g0.y - bcy;
+                const float Sx = cx * m0 - mx;
+                const float Sy = cy * m0 - my;
+                float ua, ub;
+                int sa, sb;
+                if (ft == 0) {
+                    ua = m0; sa = 5;                                                  // dL/dopacity
+                    ub = -o * half_W * (conx * Sx + cony * Sy); sb = 0;               // dL/dmean2D.x
+                } else if (ft == 1) {
+                    const float Sxx = cx * cx * m0 - 2.f * cx * mx + mxx;
+                    ua = -o * half_H * (conz * Sy + cony * Sx); sa = 1;               // dL/dmean2D.y
+                    ub = -0.5f * o * Sxx; sb = 2;                                     // dL/dconic.x
+                } else {
+                    const float Sxy = cx * cy * m0 - cx * my - cy * mx + mxy;
+                    const float Syy = cy * cy * m0 - 2.f * cy * my + myy;
+                    ua = -0.5f * o * Sxy; sa = 3;                                     // dL/dconic.y
+                    ub = -0.5f * o * Syy; sb = 4;                                     // dL/dconic.w
+                }
+                red_add(ggrad + (size_t)id * GG_STRIDE + sa, ua);
+                red_add(ggrad + (size_t)id * GG_STRIDE + sb, ub);
+            }
+        }
+        __syncwarp();   // every lane is done with the tiles and the table slots before they are overwritten
+    };
+
+    int ntab = 0;   // candidates waiting in table slots [0, ntab)
+    for (int c = 0; c < nchunk; c++) {
+        // the next chunk's id, then its record, are in flight while this chunk is worked on
+        const int pos_nxt = (c + 1 < nchunk) ? chunk_pos(c + 1) : -1;
+        const uint32_t id_nxt = pos_nxt >= 0 ? point_list[range.x + pos_nxt] : 0u;
+
+        // block-level candidate test (candidate.cuh), lane = splat; survivors join the table in list order
+        const bool keep = pos_cur >= 0 && !block_rejects(r0_cur, r1_cur, bx0, bx1, by0, by1);
+        const uint32_t km = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int slot = ntab + __popc(km & lt);
+            sm.ctab[slot][0] = r0_cur;
+            sm.ctab[slot][1] = r1_cur;
+            sm.cid[slot] = id_cur;
+            sm.cpos[slot] = pos_cur;
+        }
+        ntab += __popc(km);
+        float4 r0_nxt = make_float4(0.f, 0.f, 0.f, 0.f), r1_nxt = r0_nxt;
+        if (pos_nxt >= 0) {
+            r0_nxt = __ldg(reinterpret_cast<const float4*>(geo + 8 * (size_t)id_nxt));
+            r1_nxt = __ldg(reinterpret_cast<const float4*>(geo + 8 * (size_t)id_nxt + 4));
+        }
+        __syncwarp();
+
+        // full groups now, the rest is carried over (the last chunk flushes everything)
+        int gs = 0;
+        const bool last = (c + 1 == nchunk);
+        while (ntab - gs >= BW_N || (last && ntab - gs > 0)) {
+            process_group(gs, min(BW_N, ntab - gs));
+            gs += BW_N;
+        }
+        if (gs > 0 && gs < ntab) {   // carry the leftovers (< 8) to the front: sources are slots >= 8, destinations < 7
+            const int left = ntab - gs;
+            float4 a0, a1;
+            uint32_t ci = 0;
+            int cp = 0;
+            if (lane < left) { a0 = sm.ctab[gs + lane][0]; a1 = sm.ctab[gs + lane][1]; ci = sm.cid[gs + lane]; cp = sm.cpos[gs + lane]; }
+            __syncwarp();
+            if (lane < left) { sm.ctab[lane][0] = a0; sm.ctab[lane][1] = a1; sm.cid[lane] = ci; sm.cpos[lane] = cp; }
+            __syncwarp();
+        }
+        ntab = (gs >= ntab) ? 0 : ntab - gs;
+
+        pos_cur = pos_nxt;
+        id_cur = id_nxt;
+        r0_cur = r0_nxt;
+        r1_cur = r1_nxt;
+    }
+}
+
+}  // namespace sagars

@@ -1,0 +1,256 @@
+// render_forward_warp_kernels.cuh -- the device code of render_forward_warp.cu (see there).  Free of host-side runtime calls
+// so that tests/test_warp_kernels_emulated.py can compile it for the CPU against tests/cuda_emu/.
+#pragma once
+#include "common.cuh"
+#include "candidate.cuh"
+#include "mma.cuh"
+
+#ifndef SAGARS_DYNAMIC_SMEM
+#define SAGARS_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+namespace sagars {
+
+
+constexpr int FW_N = 8;      // candidates per group = k extent of one mma step
+constexpr int FW_TAB = 40;   // candidate table: up to 7 carried over + 32 new
+
+template <int NQ>
+struct FwCfg {
+    static constexpr int NQE = NQ < 2 ? 2 : NQ;                 // quads per feature row (power of two)
+    static constexpr int ROW = 4 * NQE;                         // padded channel count
+    static constexpr int NT = ROW / 8;                          // 8-channel n-tiles
+    static constexpr int RS = (ROW == 16) ? 24 : ROW;           // row stride of the feature tile (floats)
+    static constexpr bool ROT = ROW >= 32;                      // rotate row r by 8 r channels (conflict-free fragment loads)
+};
+
+template <int NQ>
+struct FwSmem {
+    float rowW[FW_N][32];                 // weight of candidate r for pixel p at (p + 8 r) & 31
+    float F[FW_N][FwCfg<NQ>::RS];         // gathered feature rows (rotated, see FwCfg)
+    float4 ctab[FW_TAB][2];               // candidate records (x, y, cx, cy | cz, opacity, accept_threshold, -), list order
+    uint32_t cid[FW_TAB];                 // their Gaussian ids
+    int32_t cpos[FW_TAB];                 // their positions in the tile's list
+};
+
+// NQ : float4 groups covering the K colour channels;  VEC: K % 4 == 0 -> feature rows are read as float4
+template <int NQ, bool VEC>
+__global__ void __launch_bounds__(32, (NQ <= 8) ? 28 : 12)
+render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int K,
+                           const float* __restrict__ geo, const float* __restrict__ features, const float* __restrict__ bg,
+                           float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color)
+{
+    using Cfg = FwCfg<NQ>;
+    constexpr int NQE = Cfg::NQE, ROW = Cfg::ROW, NT = Cfg::NT, RS = Cfg::RS;
+    SAGARS_DYNAMIC_SMEM(smem_raw);
+    FwSmem<NQ>& sm = *reinterpret_cast<FwSmem<NQ>*>(smem_raw);
+
+    const int lane = threadIdx.x;
+    const int tiles_x = (int)(gridDim.x >> 1);
+    const uint32_t blk_x0 = blockIdx.x * 8, blk_y0 = blockIdx.y * 4;
+    const uint32_t px = blk_x0 + (lane & 7), py = blk_y0 + (lane >> 3);
+    const bool inside = px < (uint32_t)W && py < (uint32_t)H;
+    const uint32_t pix_id = (uint32_t)W * py + px;
+    float pixx = (float)px, pixy = (float)py;
+    SAGARS_PIN_F2(pixx, pixy);   // keep nvcc from rematerialising them in the hot loop
+
+    const uint2 range = ranges[(blockIdx.y >> 2) * tiles_x + (blockIdx.x >> 1)];
+    const int total = (int)(range.y - range.x);
+    const int nchunk = (total + 31) >> 5;
+
+    float T = 1.0f;
+    uint32_t last_contributor = 0;
+    bool done = !inside;
+
+    float acc[2][NT][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+
+    const int fg = lane >> 2, ft = lane & 3;
+    const float bx0 = (float)blk_x0, bx1 = bx0 + 7.f, by0 = (float)blk_y0, by1 = by0 + 3.f;   // block of pixel centres
+    const uint32_t lt = (1u << lane) - 1u;
+    float* const rowW = &sm.rowW[0][0];
+    float* const Ft = &sm.F[0][0];
+
+    // one group: candidates in table slots [gs, gs + m), m <= 8
+    auto process_group = [&](int gs, int m) {
+        // ---- feature rows of the group: the loads are issued now and land in the F tile after the scalar loop ----
+        constexpr int QR = ROW / 4;
+        constexpr int NLD = (FW_N * QR + 31) / 32;
+        float4 fv[NLD];
+#pragma unroll
+        for (int l = 0; l < NLD; l++) {
+            const int idx = lane + 32 * l;
+            fv[l] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < FW_N * QR) {
+                const int r = idx / QR, qd = idx - r * QR;
+                const uint32_t id = sm.cid[gs + min(r, m - 1)];
+                const int c0 = 4 * qd;
+                if (VEC) {
+                    if (c0 < K) fv[l] = __ldg(reinterpret_cast<const float4*>(features + (size_t)id * K + c0));
+                } else {
+                    const float* f = features + (size_t)id * K;
+                    if (c0 + 0 < K) fv[l].x = __ldg(f + c0 + 0);
+                    if (c0 + 1 < K) fv[l].y = __ldg(f + c0 + 1);
+                    if (c0 + 2 < K) fv[l].z = __ldg(f + c0 + 2);
+                    if (c0 + 3 < K) fv[l].w = __ldg(f + c0 + 3);
+                }
+            }
+        }
+        // ---- thread = pixel over the group's candidates (the reference's chain): w -> row i of the W tile ----
+#pragma unroll 1
+        for (int i = 0; i < FW_N; i++) {
+            float w = 0.f;
+            if (i < m) {
+                const float4 g0 = sm.ctab[gs + i][0];
+                const float4 g1 = sm.ctab[gs + i][1];
+                const float dx = g0.x - pixx, dy = g0.y - pixy;
+                const float pw = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
+                if (!done && !(pw > 0.0f) && (pw >= g1.z)) {
+                    const float alpha = fminf(0.99f, g1.y * expf(pw));
+                    if (!(alpha < 1.0f / 255.0f)) {
+                        const float test_T = T * (1 - alpha);
+                        if (test_T < 0.0001f) {
+                            done = true;
+                        } else {
+                            w = alpha * T;
+                            T = test_T;
+                            last_contributor = (uint32_t)(sm.cpos[gs + i] + 1);
+                        }
+                    }
+                }
+            }
+            rowW[i * 32 + ((lane + 8 * i) & 31)] = w;
+        }
+#pragma unroll
+        for (int l = 0; l < NLD; l++) {
+            const int idx = lane + 32 * l;
+            if (idx < FW_N * QR) {
+                const int r = idx / QR, qd = idx - r * QR;
+                const int qs = Cfg::ROT ? ((qd + 2 * r) & (NQE - 1)) : qd;
+                *reinterpret_cast<float4*>(Ft + r * RS + 4 * qs) = fv[l];
+            }
+        }
+        __syncwarp();
+        // ---- C (32 pixels x C) += W^T (32 x 8) F (8 x C), 3xTF32 ----
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+            // a0 = (pixel 16 mt + fg, candidate ft), a1 = (pixel + 8, ft), a2 = (pixel, ft + 4), a3 = (pixel + 8, ft + 4)
+            const int pa = 16 * mt + fg, pb = pa + 8;
+            split_tf32(rowW[ft * 32 + ((pa + 8 * ft) & 31)], ah[mt][0], al[mt][0]);
+            split_tf32(rowW[ft * 32 + ((pb + 8 * ft) & 31)], ah[mt][1], al[mt][1]);
+            split_tf32(rowW[(ft + 4) * 32 + ((pa + 8 * ft) & 31)], ah[mt][2], al[mt][2]);   // 8 (ft + 4) = 8 ft (mod 32)
+            split_tf32(rowW[(ft + 4) * 32 + ((pb + 8 * ft) & 31)], ah[mt][3], al[mt][3]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) {
+            // b0 = (candidate ft, channel 8 nt + fg), b1 = (candidate ft + 4, same channel)
+            const int ch = 8 * nt + fg;
+            const int c0 = Cfg::ROT ? ((ch + 8 * ft) & (ROW - 1)) : ch;
+            uint32_t bh0, bl0, bh1, bl1;
+            split_tf32(Ft[ft * RS + c0], bh0, bl0);
+            split_tf32(Ft[(ft + 4) * RS + (Cfg::ROT ? ((ch + 8 * (ft + 4)) & (ROW - 1)) : ch)], bh1, bl1);
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) {
+                mma_16n8k8(acc[mt][nt], al[mt][0], al[mt][1], al[mt][2], al[mt][3], bh0, bh1);
+                mma_16n8k8(acc[mt][nt], ah[mt][0], ah[mt][1], ah[mt][2], ah[mt][3], bl0, bl1);
+                mma_16n8k8(acc[mt][nt], ah[mt][0], ah[mt][1], ah[mt][2], ah[mt][3], bh0, bh1);
+            }
+        }
+        __syncwarp();   // the tiles and the table slots may be overwritten
+    };
+
+    if (nchunk > 0) {
+        int pos_cur = lane;
+        uint32_t id_cur = pos_cur < total ? point_list[range.x + pos_cur] : 0u;
+        float4 r0_cur = __ldg(reinterpret_cast<const float4*>(geo + 8 * (size_t)id_cur));
+        float4 r1_cur = __ldg(reinterpret_cast<const float4*>(geo + 8 * (size_t)id_cur + 4));
+        int ntab = 0;   // candidates waiting in table slots [0, ntab)
+        for (int c = 0; c < nchunk; c++) {
+            if (__all_sync(0xffffffffu, done)) { ntab = 0; break; }   // the block is saturated: nothing later can contribute
+            // the next chunk's id, then its record, are in flight while this chunk is worked on
+            const int pos_nxt = 32 * (c + 1) + lane;
+            const bool has_nxt = pos_nxt < total;
+            const uint32_t id_nxt = has_nxt ? point_list[range.x + pos_nxt] : 0u;
+
+            // block-level candidate test (candidate.cuh), lane = splat; survivors join the table in list order
+            const bool keep = pos_cur < total && !block_rejects(r0_cur, r1_cur, bx0, bx1, by0, by1);
+            const uint32_t km = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int slot = ntab + __popc(km & lt);
+                sm.ctab[slot][0] = r0_cur;
+                sm.ctab[slot][1] = r1_cur;
+                sm.cid[slot] = id_cur;
+                sm.cpos[slot] = pos_cur;
+            }
+            ntab += __popc(km);
+            float4 r0_nxt = make_float4(0.f, 0.f, 0.f, 0.f), r1_nxt = r0_nxt;
+            if (has_nxt) {
+                r0_nxt = __ldg(reinterpret_cast<const float4*>(geo + 8 * (size_t)id_nxt));
+                r1_nxt = __ldg(reinterpret_cast<const float4*>(geo + 8 * (size_t)id_nxt + 4));
+            }
+            __syncwarp();
+
+            // full groups now, the rest is carried over (the last chunk flushes everything)
+            int gs = 0;
+            const bool last = (c + 1 == nchunk);
+            while (ntab - gs >= FW_N || (last && ntab - gs > 0)) {
+                process_group(gs, min(FW_N, ntab - gs));
+                gs += FW_N;
+            }
+            if (gs > 0 && gs < ntab) {   // carry the leftovers (< 8) to the front: sources are slots >= 8, destinations < 7
+                const int left = ntab - gs;
+                float4 a0, a1;
+                uint32_t ci = 0;
+                int cp = 0;
+                if (lane < left) { a0 = sm.ctab[gs + lane][0]; a1 = sm.ctab[gs + lane][1]; ci = sm.cid[gs + lane]; cp = sm.cpos[gs + lane]; }
+                __syncwarp();
+                if (lane < left) { sm.ctab[lane][0] = a0; sm.ctab[lane][1] = a1; sm.cid[lane] = ci; sm.cpos[lane] = cp; }
+                __syncwarp();
+            }
+            ntab = (gs >= ntab) ? 0 : ntab - gs;
+
+            pos_cur = pos_nxt;
+            id_cur = id_nxt;
+            r0_cur = r0_nxt;
+            r1_cur = r1_nxt;
+        }
+        // an early exit can leave carried candidates behind: the saturated block ignores them (they come later in the list)
+        (void)ntab;
+    }
+
+    // ---- epilogue: accumulator fragments -> planar image ----
+    if (inside) {
+        final_T[pix_id] = T;
+        n_contrib[pix_id] = last_contributor;
+    }
+    const size_t plane = (size_t)H * W;
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++) {
+        // fragment rows: block pixels 16 mt + fg (image row 2 mt, x = fg) and + 8 (image row 2 mt + 1)
+        const float Ta = __shfl_sync(0xffffffffu, T, 16 * mt + fg);
+        const float Tb = __shfl_sync(0xffffffffu, T, 16 * mt + fg + 8);
+        const uint32_t xa = blk_x0 + fg, ya = blk_y0 + 2 * mt, yb = ya + 1;
+        const bool ina = xa < (uint32_t)W && ya < (uint32_t)H, inb = xa < (uint32_t)W && yb < (uint32_t)H;
+        const size_t pa = (size_t)W * ya + xa, pb = (size_t)W * yb + xa;
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) {
+            const int ch = 8 * nt + 2 * ft;
+            if (ch < K) {
+                const float b = bg[ch];
+                if (ina) out_color[(size_t)ch * plane + pa] = acc[mt][nt][0] + Ta * b;
+                if (inb) out_color[(size_t)ch * plane + pb] = acc[mt][nt][2] + Tb * b;
+            }
+            if (ch + 1 < K) {
+                const float b = bg[ch + 1];
+                if (ina) out_color[(size_t)(ch + 1) * plane + pa] = acc[mt][nt][1] + Ta * b;
+                if (inb) out_color[(size_t)(ch + 1) * plane + pb] = acc[mt][nt][3] + Tb * b;
+            }
+        }
+    }
+}
+
+}  // namespace sagars

@@ -40,6 +40,8 @@ inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
 inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
 inline unsigned __float_as_uint(float f) { unsigned v; std::memcpy(&v, &f, 4); return v; }
+inline float __uint_as_float(unsigned v) { float f; std::memcpy(&f, &v, 4); return f; }
+inline float __frcp_rn(float x) { return 1.0f / x; }
 
 inline thread_local uint3 threadIdx, blockIdx;
 inline uint3 blockDim, gridDim;
@@ -94,16 +96,17 @@ inline T shfl_from(T v, int src_lane)
     return r;
 }
 
-// kernel<<<grid, block, smem>>>(args...) with 1-D grid and block
+// kernel<<<dim3(grid_x, grid_y), block, smem>>>(args...) with a 1-D block
 template <class K, class... A>
-void launch(unsigned grid, unsigned block, size_t smem_bytes, K kernel, A... args)
+void launch2d(unsigned grid_x, unsigned grid_y, unsigned block, size_t smem_bytes, K kernel, A... args)
 {
+    const unsigned grid = grid_x * grid_y;
     std::vector<unsigned char> smem(smem_bytes + 32);
     dynamic_smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem.data()) + 15u) & ~uintptr_t(15));
     std::vector<Warp> w((block + 31) / 32);
     warps = &w;
     blockDim = {block, 1, 1};
-    gridDim = {grid, 1, 1};
+    gridDim = {grid_x, grid_y, 1};
     outer_bar.reset((int)block);
     auto arm = [&] {
         block_bar.reset((int)block);
@@ -115,7 +118,7 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, K kernel, A... arg
         pool.emplace_back([&, t] {
             threadIdx = {t, 0, 0};
             for (unsigned b = 0; b < grid; b++) {
-                blockIdx = {b, 0, 0};
+                blockIdx = {b % grid_x, b / grid_x, 0};
                 kernel(args...);
                 if (thread_exit_hook) thread_exit_hook();
                 block_bar.drop();                  // this thread has left the kernel: later barriers do not wait for it
@@ -129,6 +132,12 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, K kernel, A... arg
     for (auto& th : pool) th.join();
     warps = nullptr;
     dynamic_smem = nullptr;
+}
+
+template <class K, class... A>
+void launch(unsigned grid, unsigned block, size_t smem_bytes, K kernel, A... args)
+{
+    launch2d(grid, 1u, block, smem_bytes, kernel, args...);
 }
 
 }  // namespace cuda_emu
@@ -149,6 +158,7 @@ inline int __syncthreads_and(int pred)
     return r;
 }
 template <class T> inline T __shfl_sync(unsigned, T v, int src) { return cuda_emu::shfl_from(v, src & 31); }
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int lane_mask) { return cuda_emu::shfl_from(v, (int)((threadIdx.x & 31) ^ lane_mask)); }
 template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned delta)
 {
     const int lane = threadIdx.x & 31;

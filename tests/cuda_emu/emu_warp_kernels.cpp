@@ -1,0 +1,53 @@
+// Host harness: the DEFAULT K = 32 blend kernels (one warp per 8x4 pixel block; seganygaussians_b200/csrc/
+// render_forward_warp_kernels.cuh, render_backward_warp_kernels.cuh) under the execution shim.  TEST INFRASTRUCTURE ONLY.
+#define SAGARS_CUDA_EMU 1
+#include <cuda_runtime.h>            // the shim (this directory comes first on the include path)
+#include "render_forward_warp_kernels.cuh"
+#include "render_backward_warp_kernels.cuh"
+#include "math.cuh"
+
+using namespace sagars;
+
+extern "C" void emu_make_geo(int P, const float* means2D, const float* conic_opacity, float* geo)
+{
+    for (int i = 0; i < P; i++) {
+        float* g = geo + 8 * (size_t)i;
+        g[0] = means2D[2 * i]; g[1] = means2D[2 * i + 1];
+        g[2] = conic_opacity[4 * i]; g[3] = conic_opacity[4 * i + 1]; g[4] = conic_opacity[4 * i + 2]; g[5] = conic_opacity[4 * i + 3];
+        g[6] = accept_threshold(g[5]); g[7] = 0.f;
+    }
+}
+
+extern "C" int emu_forward_warp(int W, int H, int K, const uint2* ranges, const uint32_t* point_list, const float* geo,
+                                const float* features, const float* bg, float* final_T, uint32_t* n_contrib, float* out_color)
+{
+    const unsigned tx = (W + TILE_X - 1) / TILE_X, ty = (H + TILE_Y - 1) / TILE_Y;
+    const bool vec = (K % 4) == 0;
+    const int nq = (K + 3) / 4;
+#define GO(NQ_, VEC_) cuda_emu::launch2d(2 * tx, 4 * ty, 32, sizeof(FwSmem<NQ_>), render_forward_warp_kernel<NQ_, VEC_>, ranges, point_list, \
+                                         W, H, K, geo, features, bg, final_T, n_contrib, out_color)
+    if (nq <= 1 && !vec) { GO(1, false); return 0; }
+    if (nq <= 2 && !vec) { GO(2, false); return 0; }
+    if (nq <= 4 && vec) { GO(4, true); return 0; }
+    if (nq <= 8 && vec) { GO(8, true); return 0; }
+#undef GO
+    return -1;
+}
+
+extern "C" int emu_backward_warp(int md, int W, int H, int K, const uint2* ranges, const uint32_t* point_list, const float* bg,
+                                 const float* geo, const float* features, const float* final_T, const uint32_t* n_contrib,
+                                 const float* dL_dpix, const float* dL_dout_mask, float* ggrad, float* dL_dcolors)
+{
+    const unsigned tx = (W + TILE_X - 1) / TILE_X, ty = (H + TILE_Y - 1) / TILE_Y;
+    const bool vec = (K % 4) == 0 && !md;
+    const int nq = (K + (md ? 1 : 0) + 3) / 4;
+#define GO(NQ_, VEC_, MD_) cuda_emu::launch2d(2 * tx, 4 * ty, 32, sizeof(BwSmem<NQ_>), render_backward_warp_kernel<NQ_, VEC_, MD_, true>, ranges, \
+                                              point_list, W, H, K, bg, geo, features, final_T, n_contrib, dL_dpix, dL_dout_mask, ggrad, dL_dcolors)
+    if (md) { if (nq <= 1) { GO(1, false, true); return 0; } return -1; }
+    if (nq <= 1 && !vec) { GO(1, false, false); return 0; }
+    if (nq <= 2 && !vec) { GO(2, false, false); return 0; }
+    if (nq <= 4 && vec) { GO(4, true, false); return 0; }
+    if (nq <= 8 && vec) { GO(8, true, false); return 0; }
+#undef GO
+    return -1;
+}
