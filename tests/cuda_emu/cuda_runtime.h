@@ -165,6 +165,7 @@ template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned delta)
     return cuda_emu::shfl_from(v, lane - (int)delta >= 0 ? lane - (int)delta : lane);
 }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 // full-mask warp votes / matches over the lanes that take part (every lane of the warp must call, as on the device)
 template <class T> inline unsigned __match_any_sync(unsigned, T v)
