@@ -42,6 +42,8 @@ WORKLOADS = {
     "c2": dict(P=1_000_000, H=1080, W=1920, K=32, desc="synthetic 1M Gaussians, 1080x1920, K=32 affinity features, 1 camera/GPU, fwd+bwd"),
     # BASELINE.json configs[2]-like (parity-test case, not the bench line): 5M Gaussians
     "c3": dict(P=5_000_000, H=1036, W=1600, K=32, desc="synthetic 5M Gaussians, 1036x1600, K=32 (garden-like), 1 camera/GPU, fwd+bwd"),
+    # configs[1] at K=3 (the BASE variant's channel count; developer A/B of the forward kernels, never a bench line)
+    "c2_k3": dict(P=1_000_000, H=1080, W=1920, K=3, desc="synthetic 1M Gaussians, 1080x1920, K=3, 1 camera/GPU, fwd+bwd"),
     # small variant for quick local checks (never a bench line)
     "tiny": dict(P=20_000, H=270, W=480, K=32, desc="tiny smoke workload"),
 }
@@ -55,7 +57,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fwd-kernel", default="default", choices=["default", "tile"], help="developer A/B switch (rasterizer.set_blend_kernels)")
+    ap.add_argument("--fwd-kernel", default="default", choices=["default", "tile", "warp_any"], help="developer A/B switch (rasterizer.set_blend_kernels)")
     ap.add_argument("--bwd-kernel", default="default", choices=["default", "tile"], help="developer A/B switch")
     ap.add_argument("--binning", default="radix", choices=["radix", "tile_sort"], help="developer A/B switch (rasterizer.set_binning)")
     return ap.parse_args()
@@ -297,7 +299,7 @@ def main():
         except Exception:
             pairs_to_last = None
     line = {
-        "metric": "fwd+bwd Gaussians*pixels/s @K=32", "value": value, "unit": "Gaussian*pixel/s",
+        "metric": f"fwd+bwd Gaussians*pixels/s @K={K}", "value": value, "unit": "Gaussian*pixel/s",
         "n_gpus": world if (use_dist or a.impl != "ours") else a.gpus, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -306,7 +308,8 @@ def main():
                    "parallelism": f"camera-dp{n_used}" + ("+allreduce(dL_dcolors)" if use_dist else ""),
                    "l2": "inputs_exceed_l2 (features 128 MB + upstream gradient 265 MB + image 265 MB >> 126 MB L2)",
                    "P_visible": radii_vis, "R_instances": R_inst,
-                   "kernels": {"forward": "mma.sync warp kernel" if a.fwd_kernel == "default" else "tcgen05 tile kernel",
+                   "kernels": {"forward": {"default": "mma.sync warp kernel at K=32, fp32 tile kernel otherwise", "tile": "tcgen05 tile kernel",
+                                           "warp_any": "mma.sync warp kernel for every K"}[a.fwd_kernel],
                                "backward": "mma.sync warp kernel" if a.bwd_kernel == "default" else "mma.sync tile kernel",
                                "binning": a.binning},
                    "S_pair_tests_upper_bound": S_pairs, "pairs_up_to_last_contributor": pairs_to_last},

@@ -14,5 +14,8 @@ echo "== bench: tile_sort ==";      timeout 200 python bench.py --steps 20 --war
 echo "== bench c3-like: default / tile_sort (5M Gaussians: the binning-dominated case) =="
 timeout 300 python bench.py --workload c3 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_c3_default.json 2>/dev/null; tail -c 700 gpurun_out/r2_bench_c3_default.json
 timeout 300 python bench.py --workload c3 --steps 10 --warmup 3 --no-cpu-baseline --binning tile_sort > gpurun_out/r2_bench_c3_tile_sort.json 2>/dev/null; tail -c 700 gpurun_out/r2_bench_c3_tile_sort.json
+echo "== K=3 forward: fp32 tile kernel (default) vs warp kernel =="
+timeout 200 python bench.py --workload c2_k3 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_k3_default.json 2>/dev/null; tail -c 600 gpurun_out/r2_bench_k3_default.json
+timeout 200 python bench.py --workload c2_k3 --steps 20 --warmup 5 --no-cpu-baseline --fwd-kernel warp_any > gpurun_out/r2_bench_k3_warp_any.json 2>/dev/null; tail -c 600 gpurun_out/r2_bench_k3_warp_any.json
 echo "== staging A/B (fp32 tile forward) =="; timeout 400 python tools/gpu_check.py --staging-ab 2>&1 | grep -E "timing|ours" | tee gpurun_out/r2_staging_ab.log
 echo "== regular GPU suite ==";     timeout 400 python -m pytest tests -m gpu -q 2>&1 | tail -4 | tee gpurun_out/r2_gpu_suite.log
