@@ -66,13 +66,18 @@ def _inputs(emu, fw, sc, K):
     return geo, feats, ranges, pl
 
 
-@pytest.mark.parametrize("case", [("k32", 500, 32, 48, 32, 5.0), ("k32_ragged", 300, 27, 41, 32, 4.0), ("k16", 300, 32, 32, 16, 5.0),
+@pytest.mark.parametrize("case", [("k32", 500, 32, 48, 32, 5.0), ("k32_ragged", 300, 27, 41, 32, 4.0), ("k32_opaque", 400, 32, 32, 32, 5.0),
+                                  ("k16", 300, 32, 32, 16, 5.0),
                                   ("k3_warp_any", 300, 32, 32, 3, 5.0)], ids=lambda c: c[0])
 def test_forward_warp_kernel(emu, case):
     name, P, H, W, K, sigma = case
     sc = synthetic.scene(P, H, W, K, sigma_px=sigma)
+    if name == "k32_opaque":
+        sc.gauss.opacities = torch.full_like(sc.gauss.opacities, 0.9995)     # 0.99 clamp, pixels saturate (early block exit)
     bg = np.linspace(0.2, 0.8, max(K, 3)).astype(np.float32)
     fw = _oracle_forward(sc, K, False, bg)
+    if name == "k32_opaque":
+        assert fw.final_T.max() < 1e-3 or (fw.n_contrib.max() < (fw.ranges[:, 1].astype(np.int64) - fw.ranges[:, 0]).max())
     assert (fw.ranges[:, 1].astype(np.int64) - fw.ranges[:, 0]).max() > 70          # several 32-entry chunks, carried leftovers
     geo, feats, ranges, pl = _inputs(emu, fw, sc, K)
     final_T = np.zeros((H, W), np.float32)
@@ -86,11 +91,14 @@ def test_forward_warp_kernel(emu, case):
 
 
 @pytest.mark.parametrize("case", [("k32", 400, 32, 40, 32, False, 5.0, False), ("k32_bg", 250, 24, 32, 32, False, 4.0, True),
+                                  ("k32_opaque", 250, 24, 32, 32, False, 4.0, True),       # alpha hits the 0.99 clamp, pixels saturate early
                                   ("k3", 300, 32, 32, 3, False, 5.0, False), ("depth_mask", 300, 32, 32, 3, True, 5.0, True)],
                          ids=lambda c: c[0])
 def test_backward_warp_kernel(emu, case):
     name, P, H, W, K, depth, sigma, with_bg = case
     sc = synthetic.scene(P, H, W, K, sigma_px=sigma)
+    if name == "k32_opaque":
+        sc.gauss.opacities = torch.full_like(sc.gauss.opacities, 0.9995)
     bg = (np.linspace(0.2, 0.8, max(K, 3)) if with_bg else np.zeros(max(K, 3))).astype(np.float32)
     fw = _oracle_forward(sc, K, depth, bg)
     dpix = np.ascontiguousarray(sc.dL_dout[:K].numpy())
