@@ -59,6 +59,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fwd-kernel", default="default", choices=["default", "tile", "warp_any"], help="developer A/B switch (rasterizer.set_blend_kernels)")
     ap.add_argument("--bwd-kernel", default="default", choices=["default", "tile"], help="developer A/B switch")
+    ap.add_argument("--overlap-allreduce", action="store_true",
+                    help="N > 1, developer switch: all-reduce on a side stream, gating only the next forward's blend stage "
+                         "(its geometry stages overlap the exchange); default: the all-reduce serialises with the step")
     ap.add_argument("--binning", default="radix", choices=["radix", "tile_sort"], help="developer A/B switch (rasterizer.set_binning)")
     return ap.parse_args()
 
@@ -201,6 +204,11 @@ def main():
         return Settings(image_height=H, image_width=W, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=bg, scale_modifier=1.0,
                         viewmatrix=view, projmatrix=proj, sh_degree=0, campos=campos, prefiltered=False, debug=False)
 
+    overlap = bool(getattr(a, "overlap_allreduce", False)) and a.impl == "ours"
+    reducer = None
+    if overlap and world > 1:
+        from seganygaussians_b200.data_parallel import FeatureGradReducer
+        reducer = FeatureGradReducer(side_stream=True)
     rs_resident = settings(view_d, proj_d, campos_d, bg_d)
     rast_resident = Rast(raster_settings=rs_resident)
     last = {}
@@ -214,7 +222,12 @@ def main():
         last["radii"] = radii
         color.backward(dL)
         if use_dist:
-            dist.all_reduce(colors.grad)
+            if reducer is not None:
+                reducer.wait()                               # at most one exchange in flight
+                reducer.reduce_async(colors.grad)            # side stream, behind everything queued so far
+                R.set_blend_wait_event(reducer.ready_event())
+            else:
+                dist.all_reduce(colors.grad)
 
     def step_e2e():
         for t in leaves:
@@ -243,6 +256,8 @@ def main():
             fn()
             if sampler is not None and (i == steps // 2 or i == steps - 1):
                 sampler.sample()          # the GPU is still executing this step's backward
+        if reducer is not None:
+            reducer.wait()                # the last exchange belongs to the timed region
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -305,7 +320,8 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "impl": a.impl,
         "config": {"workload": wl["desc"], "P": P, "H": H, "W": W, "K": K, "cameras_per_step": n_used,
-                   "parallelism": f"camera-dp{n_used}" + ("+allreduce(dL_dcolors)" if use_dist else ""),
+                   "parallelism": f"camera-dp{n_used}" + ("+allreduce(dL_dcolors)" if use_dist else "") +
+                                  ("+overlapped with the next forward's geometry stages" if reducer is not None else ""),
                    "l2": "inputs_exceed_l2 (features 128 MB + upstream gradient 265 MB + image 265 MB >> 126 MB L2)",
                    "P_visible": radii_vis, "R_instances": R_inst,
                    "kernels": {"forward": {"default": "mma.sync warp kernel at K=32, fp32 tile kernel otherwise", "tile": "tcgen05 tile kernel",

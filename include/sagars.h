@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SAGARS_ABI_VERSION 2
+#define SAGARS_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define SAGARS_API __attribute__((visibility("default")))
@@ -126,6 +126,12 @@ typedef struct sagars_forward_args {
      * results are identical either way; only the size of the binning buffer differs. */
     int32_t binning_capacity_hint;
     int32_t* binning_capacity_out; /* host, optional: capacity the binning buffer was finally laid out for */
+    /* Optional cudaEvent_t (NULL = none).  The per-tile blend -- the FIRST stage that reads colors_precomp / shs -- is made to
+     * wait for this event on `stream`; preprocess, key emission, sort and tile ranges (which read geometry only) are not.  A
+     * data-parallel trainer records the event after the all-reduce (and optimiser step) of the feature tensor on a side
+     * stream: that exchange then overlaps the geometry stages of the next forward instead of serialising with it
+     * (seganygaussians_b200/data_parallel.py).  The reference has nothing comparable (single stream, single GPU). */
+    void* blend_wait_event;
 } sagars_forward_args;
 
 /* Forward: preprocess -> scan -> duplicate keys -> radix sort -> tile ranges -> per-tile blend.
@@ -280,6 +286,11 @@ SAGARS_API void sagars_profile_enable(int on);
 SAGARS_API int sagars_profile_num_stages(void);
 SAGARS_API const char* sagars_profile_stage_name(int stage);
 SAGARS_API int sagars_profile_read(double* ms_out, int64_t* count_out, int reset);
+
+/* sizeof(sagars_forward_args) / sizeof(sagars_backward_args) as this library was compiled: a binding in another language checks
+ * its own struct layout against these before the first call. */
+SAGARS_API size_t sagars_sizeof_forward_args(void);
+SAGARS_API size_t sagars_sizeof_backward_args(void);
 
 SAGARS_API const char* sagars_last_error(void);
 SAGARS_API int sagars_abi_version(void);

@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsagars.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # flags (include/sagars.h)
 FLAG_PREFILTERED = 1
@@ -46,6 +46,7 @@ class ForwardArgs(C.Structure):
         ("viewmatrix", _fp), ("projmatrix", _fp), ("cam_pos", _fp),
         ("out_color", _fp), ("out_mask", _fp), ("out_depth", _fp), ("radii", _fp),
         ("binning_capacity_hint", C.c_int32), ("binning_capacity_out", C.POINTER(C.c_int32)),
+        ("blend_wait_event", C.c_void_p),
     ]
 
 
@@ -86,6 +87,7 @@ ABI_SYMBOLS = (
     "sagars_sort_temp_bytes", "sagars_sort_pairs", "sagars_knn_temp_bytes", "sagars_knn", "sagars_smooth_forward", "sagars_smooth_backward",
     "sagars_launch_count", "sagars_reset_launch_count",
     "sagars_profile_enable", "sagars_profile_num_stages", "sagars_profile_stage_name", "sagars_profile_read",
+    "sagars_sizeof_forward_args", "sagars_sizeof_backward_args",
     "sagars_last_error", "sagars_abi_version", "sagars_arch",
 )
 
@@ -118,6 +120,10 @@ def load() -> C.CDLL:
         if lib.sagars_abi_version() != ABI_VERSION:
             raise SagarsLibraryError(f"ABI version mismatch: library {lib.sagars_abi_version()}, binding {ABI_VERSION}")
         lib.sagars_arch.restype = C.c_char_p
+        for fn, st in (("sagars_sizeof_forward_args", ForwardArgs), ("sagars_sizeof_backward_args", BackwardArgs)):
+            getattr(lib, fn).restype = C.c_size_t
+            if getattr(lib, fn)() != C.sizeof(st):
+                raise SagarsLibraryError(f"{fn}() = {getattr(lib, fn)()} but the binding's struct has {C.sizeof(st)} bytes")
         lib.sagars_last_error.restype = C.c_char_p
         lib.sagars_launch_count.restype = C.c_int64
         lib.sagars_reset_launch_count.restype = None

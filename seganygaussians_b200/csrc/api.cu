@@ -155,6 +155,8 @@ using namespace sagars;
 extern "C" {
 
 int sagars_abi_version(void) { return SAGARS_ABI_VERSION; }
+size_t sagars_sizeof_forward_args(void) { return sizeof(sagars_forward_args); }
+size_t sagars_sizeof_backward_args(void) { return sizeof(sagars_backward_args); }
 
 void sagars_profile_enable(int on) { g_profile.store(on ? 1 : 0); }
 int sagars_profile_num_stages(void) { return ST_COUNT; }
@@ -362,6 +364,8 @@ int sagars_forward(const sagars_forward_args* a,
             { ProfScope ps(ST_RANGES, s); rc = launch_tile_ranges(n_dev, cap, num_tiles, bv.point_list_keys, im.ranges, s, debug); }
             if (rc) return rc;
         }
+        // the blend is the first stage that reads the colours / features: an optional event gates it (include/sagars.h)
+        if (a->blend_wait_event) SAGARS_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)a->blend_wait_event, 0));
         { ProfScope ps(ST_RENDER_FWD, s); rc = launch_render_forward(*a, d, g, im, bv.point_list, s, debug); }
         if (rc) return rc;
         if (!speculative) break;

@@ -49,6 +49,16 @@ class FeatureGradReducer:
             self._pending = ("work", dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         return self._pending
 
+    def ready_event(self):
+        """A CUDA event recorded behind the pending all-reduce on its stream (None when nothing is pending or the reduction
+        does not run on a side stream).  Hand it to ``rasterizer.set_blend_wait_event``: the next forward's geometry stages
+        then overlap the exchange and only its blend stage -- the first reader of the features -- waits for it."""
+        if self._pending is None or self._pending[0] != "stream":
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        return ev
+
     def wait(self):
         if self._pending is None:
             return

@@ -189,6 +189,19 @@ def set_staging(engine: str = "cp_async") -> None:
     _STAGING = engine
 
 
+_BLEND_WAIT_EVENT = None       # torch.cuda.Event the NEXT forward's blend stage waits for (set_blend_wait_event)
+
+
+def set_blend_wait_event(event) -> None:
+    """Gate the blend stage of the NEXT forward on a recorded ``torch.cuda.Event`` (``blend_wait_event`` of include/sagars.h).
+    The geometry stages (preprocess, binning) of that forward run ahead of the event; only the stage that reads the features
+    waits.  A data-parallel trainer records the event on the stream that all-reduces the feature gradient and applies the
+    optimiser step (``data_parallel.FeatureGradReducer.ready_event``): the exchange then overlaps the next forward's geometry
+    stages.  One-shot; ``None`` clears it."""
+    global _BLEND_WAIT_EVENT
+    _BLEND_WAIT_EVENT = event
+
+
 def set_binning(method: str = "radix") -> None:
     """How the (Gaussian, tile) instances are ordered: "radix" (default: the library's global radix sort of tile|depth keys) or
     "tile_sort" (``SAGARS_FLAG_TILE_SORT``: no global sort, every tile's segment is sorted by its own CTA).  Same results."""
@@ -292,6 +305,10 @@ def _forward_impl(settings, variant_flags, default_channels, means3D, sh, colors
         a.binning_capacity_hint = min(seen + seen // 4 + 4096, 2**31 - 1) if seen > 0 else 0
         cap_out = C.c_int32(0)
         a.binning_capacity_out = C.pointer(cap_out)
+        global _BLEND_WAIT_EVENT
+        gate = _BLEND_WAIT_EVENT
+        _BLEND_WAIT_EVENT = None                      # one-shot: it gates exactly the next forward
+        a.blend_wait_event = int(gate.cuda_event) if gate is not None else None
 
         scratch = _scratch_for_thread()
         scratch.begin(device)
