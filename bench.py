@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--overlap-allreduce", action="store_true",
                     help="N > 1, developer switch: all-reduce on a side stream, gating only the next forward's blend stage "
                          "(its geometry stages overlap the exchange); default: the all-reduce serialises with the step")
+    ap.add_argument("--allreduce", default="nccl", choices=["nccl", "multimem"],
+                    help="N > 1, developer switch: 'multimem' = the library's own all-reduce over the NVSwitch multicast mapping")
     ap.add_argument("--binning", default="radix", choices=["radix", "tile_sort"], help="developer A/B switch (rasterizer.set_binning)")
     return ap.parse_args()
 
@@ -209,6 +211,17 @@ def main():
     if overlap and world > 1:
         from seganygaussians_b200.data_parallel import FeatureGradReducer
         reducer = FeatureGradReducer(side_stream=True)
+    own_allreduce = None
+    if a.impl == "ours" and use_dist and a.allreduce == "multimem":
+        from seganygaussians_b200.data_parallel import MulticastAllReduce
+        own_allreduce = MulticastAllReduce(P * K, dev)
+
+    def reduce_grad(t):
+        if own_allreduce is not None:
+            own_allreduce.all_reduce_(t)
+        else:
+            dist.all_reduce(t)
+
     rs_resident = settings(view_d, proj_d, campos_d, bg_d)
     rast_resident = Rast(raster_settings=rs_resident)
     last = {}
@@ -227,7 +240,7 @@ def main():
                 reducer.reduce_async(colors.grad)            # side stream, behind everything queued so far
                 R.set_blend_wait_event(reducer.ready_event())
             else:
-                dist.all_reduce(colors.grad)
+                reduce_grad(colors.grad)
 
     def step_e2e():
         for t in leaves:
@@ -240,7 +253,7 @@ def main():
         loss = (color * dL).sum()
         loss.backward()
         if use_dist:
-            dist.all_reduce(colors.grad)
+            reduce_grad(colors.grad)
         return float(loss.item())   # device -> host read of the step's result
 
     def barrier():
@@ -321,7 +334,8 @@ def main():
         "impl": a.impl,
         "config": {"workload": wl["desc"], "P": P, "H": H, "W": W, "K": K, "cameras_per_step": n_used,
                    "parallelism": f"camera-dp{n_used}" + ("+allreduce(dL_dcolors)" if use_dist else "") +
-                                  ("+overlapped with the next forward's geometry stages" if reducer is not None else ""),
+                                  ("+overlapped with the next forward's geometry stages" if reducer is not None else "") +
+                                  (" [own multimem all-reduce]" if own_allreduce is not None else ""),
                    "l2": "inputs_exceed_l2 (features 128 MB + upstream gradient 265 MB + image 265 MB >> 126 MB L2)",
                    "P_visible": radii_vis, "R_instances": R_inst,
                    "kernels": {"forward": {"default": "mma.sync warp kernel at K=32, fp32 tile kernel otherwise", "tile": "tcgen05 tile kernel",

@@ -273,6 +273,14 @@ SAGARS_API int sagars_smooth_backward(int32_t device, int32_t P, int32_t C, int3
                                       const float* mean_norm, const float* out, const float* dL_dout,
                                       float* dL_dn_scratch, float* dL_dfeatures, void* stream);
 
+/* The library's own all-reduce (sum, fp32, in place) over an NVSwitch multicast mapping (opt-in alternative to the NCCL call of
+ * seganygaussians_b200/data_parallel.py).  `multicast_ptr` is the multicast address of a buffer of
+ * `numel` floats (numel % 4 == 0) that belongs to a symmetric allocation spanning all `world` GPUs of the process group; the
+ * caller orders it against producers and consumers of the buffer with device-side barriers of that allocation (before and
+ * after).  Rank r reduces and re-broadcasts the r-th 1/world slice with multimem.ld_reduce / multimem.st. */
+SAGARS_API int sagars_multimem_allreduce_f32(int32_t device, void* multicast_ptr, int64_t numel, int32_t rank, int32_t world,
+                                             void* stream);
+
 /* number of kernels launched by this library (process-wide) since the last reset
  * (bench.py reports it as `gpu_launches`). */
 SAGARS_API int64_t sagars_launch_count(void);

@@ -87,7 +87,7 @@ ABI_SYMBOLS = (
     "sagars_sort_temp_bytes", "sagars_sort_pairs", "sagars_knn_temp_bytes", "sagars_knn", "sagars_smooth_forward", "sagars_smooth_backward",
     "sagars_launch_count", "sagars_reset_launch_count",
     "sagars_profile_enable", "sagars_profile_num_stages", "sagars_profile_stage_name", "sagars_profile_read",
-    "sagars_sizeof_forward_args", "sagars_sizeof_backward_args",
+    "sagars_sizeof_forward_args", "sagars_sizeof_backward_args", "sagars_multimem_allreduce_f32",
     "sagars_last_error", "sagars_abi_version", "sagars_arch",
 )
 
@@ -149,6 +149,8 @@ def load() -> C.CDLL:
         lib.sagars_get_geom_layout.argtypes = [C.c_int32, C.POINTER(GeomLayout)]
         lib.sagars_get_image_layout.argtypes = [C.c_int32, C.c_int32, C.POINTER(ImageLayout)]
         lib.sagars_get_binning_layout.argtypes = [C.c_int32, C.POINTER(BinningLayout)]
+        lib.sagars_multimem_allreduce_f32.restype = C.c_int
+        lib.sagars_multimem_allreduce_f32.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
         lib.sagars_forward.restype = C.c_int
         lib.sagars_forward.argtypes = [C.POINTER(ForwardArgs), ALLOC_FN, C.c_void_p, ALLOC_FN, C.c_void_p,
                                        ALLOC_FN, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]
