@@ -7,7 +7,7 @@
 set -u
 mkdir -p gpurun_out
 export SAGARS_TEST_EXPERIMENTAL=1
-echo "== gated tests ==";          timeout 400 python -m pytest tests -m gpu -q -k "tile_sort or tma or scale_modifier" 2>&1 | tail -15 | tee gpurun_out/r2_gated_tests.log
+echo "== gated tests ==";          timeout 400 python -m pytest tests -m gpu -q -k "tile_sort or tma or scale_modifier or blend_wait" 2>&1 | tail -15 | tee gpurun_out/r2_gated_tests.log
 unset SAGARS_TEST_EXPERIMENTAL
 echo "== bench: default ==";        timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err; tail -c 1500 gpurun_out/r2_bench_default.json
 echo "== bench: tile_sort ==";      timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --binning tile_sort > gpurun_out/r2_bench_tile_sort.json 2> gpurun_out/r2_bench_tile_sort.err; tail -c 1500 gpurun_out/r2_bench_tile_sort.json
