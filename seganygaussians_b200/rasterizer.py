@@ -308,7 +308,11 @@ def _forward_impl(settings, variant_flags, default_channels, means3D, sh, colors
         global _BLEND_WAIT_EVENT
         gate = _BLEND_WAIT_EVENT
         _BLEND_WAIT_EVENT = None                      # one-shot: it gates exactly the next forward
-        a.blend_wait_event = int(gate.cuda_event) if gate is not None else None
+        if gate is not None:
+            handle = gate.cuda_event                  # cudaEvent_t of a RECORDED torch.cuda.Event (int; c_void_p in old versions)
+            a.blend_wait_event = int(getattr(handle, "value", handle))
+        else:
+            a.blend_wait_event = None
 
         scratch = _scratch_for_thread()
         scratch.begin(device)
