@@ -16,8 +16,9 @@
 //                            most once and the reference's emission order is ascending Gaussian id, so ascending
 //                            (depth bits, id) IS the stable order.  Segments of <= 1024 pairs are sorted in 8 KB of shared
 //                            memory by the tile's own CTA; longer ones are queued for a small persistent grid (<= 8192 pairs:
-//                            64 KB of shared memory; longer: in place in global memory, same network); the sorted ids and
-//                            the re-assembled keys are written once                            (8 B read + 12 B written)
+//                            64 KB of shared memory; longer: chunks of 8192 through that buffer, only the network's long-span
+//                            stages in global memory); the sorted ids and the re-assembled keys are written once
+//                                                                                              (8 B read + 12 B written)
 // The sort network is the normalised bitonic network (every comparator ascending: a "flip" stage with partner i ^ (k - 1),
 // then half-cleaners with partner i ^ j).  With all comparators ascending a segment of any length n sorts as if padded with
 // +inf to the next power of two: comparators whose upper index is >= n are skipped (sort_network.cuh; tests/test_tile_sort_network.py compiles

@@ -163,8 +163,9 @@ tile_sort_small_kernel(uint2* __restrict__ ranges, const uint64_t* __restrict__ 
     write_sorted<256>(a, n, tile, rg.x, point_list, keys);
 }
 
-// Persistent CTAs over the queue of long segments: up to TSORT_LARGE pairs in 64 KB of shared memory, longer ones in place
-// in global memory (the same network; __syncthreads orders the CTA's own global accesses between stages).
+// Persistent CTAs over the queue of long segments: up to TSORT_LARGE pairs in 64 KB of shared memory; longer ones chunk by chunk
+// through the same buffer, with only the long-span stages of the network in global memory (__syncthreads orders the CTA's own
+// global accesses between stages).
 __global__ void __launch_bounds__(1024)
 tile_sort_big_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ pairs, uint32_t* __restrict__ point_list,
                      uint64_t* __restrict__ keys, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ n_dev, int cap)
@@ -184,7 +185,39 @@ tile_sort_big_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ pa
             network_sort<1024>(sh, n);
             write_sorted<1024>(sh, n, tile, rg.x, point_list, keys);
         } else {
-            network_sort<1024>(seg, n);
+            // Longer than the shared buffer.  The network's stages with span <= TSORT_LARGE only ever pair elements of the same
+            // aligned TSORT_LARGE-chunk, so they run chunk by chunk in shared memory; only the few stages with a longer span
+            // (one flip + log2(k / TSORT_LARGE) - 1 half-cleaners per k > TSORT_LARGE) touch global memory.  Same comparators
+            // in the same order as network_sort on the whole segment -- grouped by where their operands live.
+            constexpr uint32_t CH = TSORT_LARGE;
+            const uint32_t N = network_width(n);
+            for (uint32_t base = 0; base < n; base += CH) {            // every stage with k <= CH: sort each chunk
+                const uint32_t m = n - base < CH ? n - base : CH;
+                for (uint32_t i = threadIdx.x; i < m; i += 1024) sh[i] = seg[base + i];
+                __syncthreads();
+                network_sort<1024>(sh, m);
+                for (uint32_t i = threadIdx.x; i < m; i += 1024) seg[base + i] = sh[i];
+                __syncthreads();
+            }
+            for (uint32_t k = 2 * CH; k <= N; k <<= 1) {
+                network_stage(seg, n, N, k, 0u, threadIdx.x, 1024);     // flip, span k
+                __syncthreads();
+                for (uint32_t j = k >> 2; j >= CH; j >>= 1) {           // half-cleaners that cross chunk boundaries
+                    network_stage(seg, n, N, k, j, threadIdx.x, 1024);
+                    __syncthreads();
+                }
+                for (uint32_t base = 0; base < n; base += CH) {         // strides CH/2 ... 1: inside a chunk
+                    const uint32_t m = n - base < CH ? n - base : CH;
+                    for (uint32_t i = threadIdx.x; i < m; i += 1024) sh[i] = seg[base + i];
+                    __syncthreads();
+                    for (uint32_t j = CH >> 1; j > 0; j >>= 1) {
+                        network_stage(sh, m, CH, k, j, threadIdx.x, 1024);
+                        __syncthreads();
+                    }
+                    for (uint32_t i = threadIdx.x; i < m; i += 1024) seg[base + i] = sh[i];
+                    __syncthreads();
+                }
+            }
             write_sorted<1024>(seg, n, tile, rg.x, point_list, keys);
         }
         __syncthreads();   // the shared buffer is reused by the next queue entry

@@ -60,7 +60,8 @@ CASES = [
     ("typical", 1500, 56, 72, 2.0, "small"),
     ("ragged_sparse", 120, 50, 70, 1.0, "small"),
     ("mid_segments", 2600, 32, 32, 30.0, "large"),      # tiles with 1024 < n <= 8192 instances -> queue + 64 KB shared path
-    ("huge_segments", 9000, 16, 32, 80.0, "huge"),      # n > 8192 -> in-place global-memory path
+    ("huge_segments", 9000, 16, 32, 80.0, "huge"),      # n > 8192 -> chunks through shared memory + long-span stages in global memory
+    ("huger_segments", 21000, 16, 16, 200.0, "huge"),   # one tile with ~20 k instances: k = 16384 and 32768 of the long-span path
 ]
 
 

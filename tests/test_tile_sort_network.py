@@ -27,6 +27,33 @@ extern "C" void cta_sort(uint64_t* a, uint32_t n, uint32_t nthreads)
             for (uint32_t t = 0; t < nthreads; t++) network_stage(a, n, N, k, j, t, nthreads);
     }
 }
+// the schedule tile_sort_big_kernel uses for segments longer than its shared buffer (CH pairs): stages with span <= CH chunk by
+// chunk through a scratch copy, only the longer spans on the whole array
+extern "C" void cta_sort_chunked(uint64_t* seg, uint32_t n, uint32_t nthreads, uint32_t CH)
+{
+    using namespace sagars;
+    const uint32_t N = network_width(n);
+    uint64_t* sh = new uint64_t[CH];
+    auto chunk_pass = [&](uint32_t base, auto body) {
+        const uint32_t m = n - base < CH ? n - base : CH;
+        for (uint32_t i = 0; i < m; i++) sh[i] = seg[base + i];
+        body(m);
+        for (uint32_t i = 0; i < m; i++) seg[base + i] = sh[i];
+    };
+    for (uint32_t base = 0; base < n; base += CH)
+        chunk_pass(base, [&](uint32_t m) { cta_sort(sh, m, nthreads); });
+    for (uint32_t k = 2 * CH; k <= N; k <<= 1) {
+        for (uint32_t t = 0; t < nthreads; t++) network_stage(seg, n, N, k, 0u, t, nthreads);
+        for (uint32_t j = k >> 2; j >= CH; j >>= 1)
+            for (uint32_t t = 0; t < nthreads; t++) network_stage(seg, n, N, k, j, t, nthreads);
+        for (uint32_t base = 0; base < n; base += CH)
+            chunk_pass(base, [&](uint32_t m) {
+                for (uint32_t j = CH >> 1; j > 0; j >>= 1)
+                    for (uint32_t t = 0; t < nthreads; t++) network_stage(sh, m, CH, k, j, t, nthreads);
+            });
+    }
+    delete[] sh;
+}
 // every comparator of every stage touches a distinct pair of indices (so the threads of a stage cannot race)
 extern "C" int stages_are_disjoint(uint32_t N)
 {
@@ -62,6 +89,7 @@ def lib():
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", src, "-o", so])
     L = ctypes.CDLL(so)
     L.cta_sort.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32]
+    L.cta_sort_chunked.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
     L.stages_are_disjoint.argtypes = [ctypes.c_uint32]
     L.stages_are_disjoint.restype = ctypes.c_int
     return L
@@ -91,6 +119,22 @@ def test_class_boundaries_and_long_segments(lib, n, threads):
     got = a.copy()
     lib.cta_sort(got.ctypes.data, n, threads)
     assert np.array_equal(got, np.sort(a))
+
+
+def test_chunked_schedule_for_segments_longer_than_the_shared_buffer(lib):
+    """Small chunk sizes make the long-span machinery run on short arrays: every n in a range, several chunk sizes."""
+    rng = np.random.RandomState(7)
+    for CH in (8, 32, 64):
+        for n in list(range(CH + 1, 6 * CH + 3)) + [17 * CH + 5, 33 * CH - 1]:
+            a = _pairs(rng, n, ties=(n % 3 == 0))
+            got = a.copy()
+            lib.cta_sort_chunked(got.ctypes.data, n, 16, CH)
+            assert np.array_equal(got, np.sort(a)), (CH, n)
+    for n in (8193, 20011, 70001):                       # the kernel's own chunk size
+        a = _pairs(rng, n)
+        got = a.copy()
+        lib.cta_sort_chunked(got.ctypes.data, n, 1024, 8192)
+        assert np.array_equal(got, np.sort(a)), n
 
 
 def test_already_sorted_reverse_and_constant_depth(lib):
