@@ -5,6 +5,7 @@
 // atomics), __shared__ variables are function-local statics (uninitialised across blocks, like the real thing),
 // __syncthreads / full-mask warp shuffles are barriers that tolerate threads that have already left the kernel.
 #pragma once
+#include <atomic>
 #include <condition_variable>
 #include <cstdint>
 #include <cstring>
@@ -48,25 +49,31 @@ inline uint3 blockDim, gridDim;
 
 namespace cuda_emu {
 
-// barrier over the threads of a group that are still inside the kernel
+// barrier over the threads of a group that are still inside the kernel.  The bookkeeping sits under a mutex (arrivals and
+// departures must be decided atomically together), the waiting does not: a block has up to 1024 OS threads on a handful of
+// cores, and waking them through a condition variable spent most of the suite's time in futex calls -- they yield on the
+// generation counter instead.
 struct Barrier {
     std::mutex m;
-    std::condition_variable cv;
     int active = 0, waiting = 0;
-    uint64_t gen = 0;
-    void reset(int n) { active = n; waiting = 0; }
+    std::atomic<uint64_t> gen{0};
+    void reset(int n) { std::lock_guard<std::mutex> lk(m); active = n; waiting = 0; }
     void sync()
     {
-        std::unique_lock<std::mutex> lk(m);
-        if (++waiting == active) { waiting = 0; gen++; cv.notify_all(); return; }
-        const uint64_t g = gen;
-        cv.wait(lk, [&] { return gen != g; });
+        uint64_t g;
+        {
+            std::lock_guard<std::mutex> lk(m);
+            g = gen.load();
+            if (++waiting == active) { waiting = 0; gen.store(g + 1); return; }
+        }
+        while (gen.load() == g) std::this_thread::yield();
     }
+    // a thread that has left the kernel no longer takes part; if everybody else is already waiting, let them go
     void drop()
     {
-        std::unique_lock<std::mutex> lk(m);
+        std::lock_guard<std::mutex> lk(m);
         --active;
-        if (active > 0 && waiting == active) { waiting = 0; gen++; cv.notify_all(); }
+        if (active > 0 && waiting == active) { waiting = 0; gen.fetch_add(1); }
     }
 };
 
@@ -157,16 +164,32 @@ inline int __syncthreads_and(int pred)
     __atomic_store_n(&f, 0, __ATOMIC_RELAXED);
     return r;
 }
-template <class T> inline T __shfl_sync(unsigned, T v, int src) { return cuda_emu::shfl_from(v, src & 31); }
-template <class T> inline T __shfl_xor_sync(unsigned, T v, int lane_mask) { return cuda_emu::shfl_from(v, (int)((threadIdx.x & 31) ^ lane_mask)); }
+// width: the warp is split into segments of `width` lanes and the source lane is taken inside the caller's segment
+template <class T> inline T __shfl_sync(unsigned, T v, int src, int width = 32)
+{
+    const int lane = threadIdx.x & 31;
+    return cuda_emu::shfl_from(v, (lane & ~(width - 1)) | (src & (width - 1)));
+}
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int lane_mask, int width = 32)
+{
+    const int lane = threadIdx.x & 31, src = lane ^ lane_mask;
+    return cuda_emu::shfl_from(v, (src & ~(width - 1)) == (lane & ~(width - 1)) ? src : lane);
+}
 template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned delta)
 {
     const int lane = threadIdx.x & 31;
     return cuda_emu::shfl_from(v, lane - (int)delta >= 0 ? lane - (int)delta : lane);
 }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicMax(unsigned* p, unsigned v)
+{
+    unsigned old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
 inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
 // full-mask warp votes / matches over the lanes that take part (every lane of the warp must call, as on the device)
 template <class T> inline unsigned __match_any_sync(unsigned, T v)
 {

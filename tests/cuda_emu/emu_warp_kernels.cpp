@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>            // the shim (this directory comes first on the include path)
 #include "render_forward_warp_kernels.cuh"
 #include "render_backward_warp_kernels.cuh"
+#include "render_backward_kernels.cuh"
+#include "render_backward_mma_kernels.cuh"
 #include "math.cuh"
 
 using namespace sagars;
@@ -49,5 +51,32 @@ extern "C" int emu_backward_warp(int md, int W, int H, int K, const uint2* range
     if (nq <= 4 && vec) { GO(4, true, false); return 0; }
     if (nq <= 8 && vec) { GO(8, true, false); return 0; }
 #undef GO
+    return -1;
+}
+
+// the two CTA-per-tile backward kernels: kind 1 = fp32 SIMT (render_backward_kernels.cuh), kind 2 = mma.sync tile kernel
+extern "C" int emu_backward_tile(int kind, int md, int W, int H, int K, const uint2* ranges, const uint32_t* point_list, const float* bg,
+                                 const float* geo, const float* features, const float* final_T, const uint32_t* n_contrib,
+                                 const float* dL_dpix, const float* dL_dout_mask, float* ggrad, float* dL_dcolors)
+{
+    cuda_emu::thread_exit_hook = emu_async::flush_thread;
+    const unsigned tx = (W + TILE_X - 1) / TILE_X, ty = (H + TILE_Y - 1) / TILE_Y;
+    const bool vec = (K % 4) == 0 && !md;
+    const int nq = (K + (md ? 1 : 0) + 3) / 4;
+#define GO1(NQ_, VEC_, MD_) cuda_emu::launch2d(tx, ty, TILE_PIX, sizeof(BwdSmem<NQ_>), render_backward_kernel<NQ_, VEC_, MD_, true>, ranges, point_list, \
+                                               W, H, K, bg, geo, features, final_T, n_contrib, dL_dpix, dL_dout_mask, ggrad, dL_dcolors)
+#define GO2(NQ_, VEC_, MD_) cuda_emu::launch2d(tx, ty, TILE_PIX, sizeof(BmSmem<NQ_>), render_backward_mma_kernel<NQ_, VEC_, MD_, true>, ranges, point_list, \
+                                               W, H, K, bg, geo, features, final_T, n_contrib, dL_dpix, dL_dout_mask, ggrad, dL_dcolors)
+    if (kind == 1) {
+        if (md) { if (nq <= 1) { GO1(1, false, true); return 0; } return -1; }
+        if (nq <= 1 && !vec) { GO1(1, false, false); return 0; }
+        if (nq <= 8 && vec) { GO1(8, true, false); return 0; }
+    } else if (kind == 2) {
+        if (md) { if (nq <= 1) { GO2(1, false, true); return 0; } return -1; }
+        if (nq <= 1 && !vec) { GO2(1, false, false); return 0; }
+        if (nq <= 8 && vec) { GO2(8, true, false); return 0; }
+    }
+#undef GO1
+#undef GO2
     return -1;
 }

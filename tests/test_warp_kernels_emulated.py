@@ -35,6 +35,8 @@ def emu():
     L.emu_forward_warp.argtypes = [C.c_int] * 3 + [C.c_void_p] * 8
     L.emu_backward_warp.restype = C.c_int
     L.emu_backward_warp.argtypes = [C.c_int] * 4 + [C.c_void_p] * 11
+    L.emu_backward_tile.restype = C.c_int
+    L.emu_backward_tile.argtypes = [C.c_int] * 5 + [C.c_void_p] * 11
     L.emu_make_geo.argtypes = [C.c_int] + [C.c_void_p] * 3
     return L
 
@@ -66,7 +68,7 @@ def _inputs(emu, fw, sc, K):
     return geo, feats, ranges, pl
 
 
-@pytest.mark.parametrize("case", [("k32", 500, 32, 48, 32, 5.0), ("k32_ragged", 300, 27, 41, 32, 4.0), ("k32_opaque", 400, 32, 32, 32, 5.0),
+@pytest.mark.parametrize("case", [("k32", 260, 32, 32, 32, 5.0), ("k32_ragged", 200, 27, 41, 32, 4.0), ("k32_opaque", 260, 32, 32, 32, 5.0),
                                   ("k16", 300, 32, 32, 16, 5.0),
                                   ("k3_warp_any", 300, 32, 32, 3, 5.0)], ids=lambda c: c[0])
 def test_forward_warp_kernel(emu, case):
@@ -90,11 +92,15 @@ def test_forward_warp_kernel(emu, case):
     np.testing.assert_allclose(color, fw.color, rtol=5e-6, atol=5e-7)
 
 
-@pytest.mark.parametrize("case", [("k32", 400, 32, 40, 32, False, 5.0, False), ("k32_bg", 250, 24, 32, 32, False, 4.0, True),
-                                  ("k32_opaque", 250, 24, 32, 32, False, 4.0, True),       # alpha hits the 0.99 clamp, pixels saturate early
+@pytest.mark.parametrize("case", [("k32", 220, 32, 32, 32, False, 5.0, False), ("k32_bg", 160, 24, 32, 32, False, 4.0, True),
+                                  ("k32_opaque", 160, 24, 32, 32, False, 4.0, True),       # alpha hits the 0.99 clamp, pixels saturate early
                                   ("k3", 300, 32, 32, 3, False, 5.0, False), ("depth_mask", 300, 32, 32, 3, True, 5.0, True)],
                          ids=lambda c: c[0])
-def test_backward_warp_kernel(emu, case):
+@pytest.mark.parametrize("kind", ["warp", "simt_tile", "mma_tile"])
+def test_backward_kernels(emu, case, kind):
+    """kind: the default warp-per-block kernel, and the two CTA-per-tile alternates (fp32 SIMT behind
+    SAGARS_FLAG_NO_TENSOR_CORES -- csrc/render_backward_kernels.cuh; mma.sync behind SAGARS_FLAG_BWD_TILE --
+    csrc/render_backward_mma_kernels.cuh)."""
     name, P, H, W, K, depth, sigma, with_bg = case
     sc = synthetic.scene(P, H, W, K, sigma_px=sigma)
     if name == "k32_opaque":
@@ -109,8 +115,12 @@ def test_backward_warp_kernel(emu, case):
     dcol = np.zeros((P, K), np.float32)
     final_T = np.ascontiguousarray(fw.final_T.astype(np.float32))
     n_contrib = np.ascontiguousarray(fw.n_contrib.astype(np.uint32))
-    rc = emu.emu_backward_warp(int(depth), W, H, K, _p(ranges), _p(pl), _p(bg), _p(geo), _p(feats), _p(final_T), _p(n_contrib),
-                               _p(dpix), _p(dmask), _p(ggrad), _p(dcol))
+    if kind == "warp":
+        rc = emu.emu_backward_warp(int(depth), W, H, K, _p(ranges), _p(pl), _p(bg), _p(geo), _p(feats), _p(final_T), _p(n_contrib),
+                                   _p(dpix), _p(dmask), _p(ggrad), _p(dcol))
+    else:
+        rc = emu.emu_backward_tile(1 if kind == "simt_tile" else 2, int(depth), W, H, K, _p(ranges), _p(pl), _p(bg), _p(geo), _p(feats),
+                                   _p(final_T), _p(n_contrib), _p(dpix), _p(dmask), _p(ggrad), _p(dcol))
     assert rc == 0
 
     def close(got, want, what):
