@@ -23,14 +23,18 @@ from oracle import oracle as orc
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def emu():
+# "packed": the opt-in build variant -DSAGARS_PACK_CPOS (a candidate's list position rides in the unused 8th float of its record
+# in the warp kernels' candidate tables; 61 -> 55 instructions in the forward's scalar loop, not yet run on a GPU)
+@pytest.fixture(scope="module", params=["default", "packed"])
+def emu(request):
     d = tempfile.mkdtemp(prefix="sagars_emu_")
     so = os.path.join(d, "libemu_warp.so")
-    subprocess.check_call(["g++", "-O1", "-std=c++20", "-pthread", "-ffp-contract=off", "-shared", "-fPIC",
-                           "-I", os.path.join(ROOT, "tests", "cuda_emu"), "-I", os.path.join(ROOT, "seganygaussians_b200", "csrc"),
+    extra = ["-DSAGARS_PACK_CPOS"] if request.param == "packed" else []
+    subprocess.check_call(["g++", "-O1", "-std=c++20", "-pthread", "-ffp-contract=off", "-shared", "-fPIC"] + extra +
+                          ["-I", os.path.join(ROOT, "tests", "cuda_emu"), "-I", os.path.join(ROOT, "seganygaussians_b200", "csrc"),
                            os.path.join(ROOT, "tests", "cuda_emu", "emu_warp_kernels.cpp"), "-o", so])
     L = C.CDLL(so)
+    L.variant = request.param
     L.emu_forward_warp.restype = C.c_int
     L.emu_forward_warp.argtypes = [C.c_int] * 3 + [C.c_void_p] * 8
     L.emu_backward_warp.restype = C.c_int
@@ -102,6 +106,8 @@ def test_backward_kernels(emu, case, kind):
     SAGARS_FLAG_NO_TENSOR_CORES -- csrc/render_backward_kernels.cuh; mma.sync behind SAGARS_FLAG_BWD_TILE --
     csrc/render_backward_mma_kernels.cuh)."""
     name, P, H, W, K, depth, sigma, with_bg = case
+    if emu.variant == "packed" and kind != "warp":
+        pytest.skip("the build variant only touches the warp-per-block kernels")
     sc = synthetic.scene(P, H, W, K, sigma_px=sigma)
     if name == "k32_opaque":
         sc.gauss.opacities = torch.full_like(sc.gauss.opacities, 0.9995)
