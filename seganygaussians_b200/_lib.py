@@ -11,7 +11,9 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsagars.so")
+_DEFAULT_LIB_PATH = os.path.join(_HERE, "lib", "libsagars.so")
+# SAGARS_LIBRARY: developer switch to load a differently built libsagars.so (a build variant under lib/variants/); never a fallback
+LIB_PATH = os.environ.get("SAGARS_LIBRARY") or _DEFAULT_LIB_PATH
 
 ABI_VERSION = 3
 

@@ -18,11 +18,12 @@ echo "== K=3 forward: fp32 tile kernel (default) vs warp kernel =="
 timeout 200 python bench.py --workload c2_k3 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_k3_default.json 2>/dev/null; tail -c 600 gpurun_out/r2_bench_k3_default.json
 timeout 200 python bench.py --workload c2_k3 --steps 20 --warmup 5 --no-cpu-baseline --fwd-kernel warp_any > gpurun_out/r2_bench_k3_warp_any.json 2>/dev/null; tail -c 600 gpurun_out/r2_bench_k3_warp_any.json
 echo "== staging A/B (fp32 tile forward) =="; timeout 400 python tools/gpu_check.py --staging-ab 2>&1 | grep -E "timing|ours" | tee gpurun_out/r2_staging_ab.log
-echo "== build variant -DSAGARS_PACK_CPOS: parity subset + bench (the default library is restored afterwards) =="
-cp seganygaussians_b200/lib/libsagars.so /tmp/libsagars.default.so
-if make -C seganygaussians_b200/csrc clean all EXTRA_NVCCFLAGS=-DSAGARS_PACK_CPOS -j8 > gpurun_out/r2_pack_build.log 2>&1; then
-  timeout 300 python -m pytest tests/test_parity_gpu.py -m gpu -q -x 2>&1 | tail -3 | tee gpurun_out/r2_pack_parity.log
-  timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_pack_cpos.json 2>/dev/null; tail -c 900 gpurun_out/r2_bench_pack_cpos.json
+echo "== build variant pack_cpos (make -C seganygaussians_b200/csrc variants, run BEFORE gpurun): parity subset + bench =="
+VARIANT=$PWD/seganygaussians_b200/lib/variants/pack_cpos/libsagars.so
+if [ -f "$VARIANT" ]; then
+  SAGARS_LIBRARY=$VARIANT timeout 300 python -m pytest tests/test_parity_gpu.py -m gpu -q -x 2>&1 | tail -3 | tee gpurun_out/r2_pack_parity.log
+  SAGARS_LIBRARY=$VARIANT timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_pack_cpos.json 2>/dev/null; tail -c 900 gpurun_out/r2_bench_pack_cpos.json
+else
+  echo "(not built: run make -C seganygaussians_b200/csrc variants first)"
 fi
-make -C seganygaussians_b200/csrc clean all -j8 > /dev/null 2>&1 || cp /tmp/libsagars.default.so seganygaussians_b200/lib/libsagars.so
 echo "== regular GPU suite ==";     timeout 400 python -m pytest tests -m gpu -q 2>&1 | tail -4 | tee gpurun_out/r2_gpu_suite.log
