@@ -65,3 +65,33 @@ def test_emulated_default_binning_reproduces_the_oracle(emu, case):
     assert np.array_equal(keys[:R], o.keys)
     assert np.array_equal(vals[:R], o.point_list)
     assert np.array_equal(ranges, o.ranges)
+
+
+def test_speculative_layout_of_the_default_path(emu):
+    """Capacity hint larger than the count: same result in the first R slots; hint too small: the kernels must not write a single
+    key, value or range (api.cu then re-issues the stages with the exact size)."""
+    P, H, W = 900, 48, 64
+    sc = synthetic.scene(P, H, W, 3, sigma_px=3.0)
+    o = common.run_oracle(sc, 3, backward=False)
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    R = o.num_rendered
+    geo = np.zeros((P, 8), np.float32)
+    geo[:, 0:2] = o.means2D
+    tt = np.ascontiguousarray(o.tiles_touched.astype(np.uint32))
+    depths = np.ascontiguousarray(o.depths.astype(np.float32))
+    radii = np.ascontiguousarray(o.radii.astype(np.int32))
+    p = lambda a: a.ctypes.data
+    for cap, expect_written in ((R + R // 4 + 4096, True), (R - 1, False)):
+        point_offsets = np.zeros(P, np.uint32)
+        keys = np.full(cap + 1, 0xFFFFFFFFFFFFFFFF, np.uint64)
+        vals = np.full(cap + 1, 0xFFFFFFFF, np.uint32)
+        ranges = np.zeros((gx * gy, 2), np.uint32)
+        nr = np.zeros(1, np.uint32)
+        rc = emu.emu_binning(P, p(geo), p(depths), p(tt), p(radii), gx, gy, 32 + _higher_msb(gx * gy), cap, R,
+                             p(point_offsets), p(keys), p(vals), p(ranges), p(nr))
+        assert rc == 0 and int(nr[0]) == R
+        assert np.array_equal(point_offsets, o.point_offsets)          # written either way (they do not live in the binning buffer)
+        if expect_written:
+            assert np.array_equal(keys[:R], o.keys) and np.array_equal(vals[:R], o.point_list) and np.array_equal(ranges, o.ranges)
+        else:
+            assert np.all(keys == 0xFFFFFFFFFFFFFFFF) and np.all(vals == 0xFFFFFFFF) and not ranges.any()
