@@ -36,6 +36,7 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn, int b_
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+#if !defined(SAGARS_CUDA_EMU)
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p; }"
@@ -104,8 +105,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v)
 // 128-thread named barrier (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void bar_sync_128(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
+#endif  // SAGARS_CUDA_EMU (tests/cuda_emu/tc_emu.h restates the functions above for the CPU execution shim)
+
 // split an fp32 value into a tf32-exact high part and the remainder (kept to ~22 significant bits by the MMA)
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 }  // namespace tc
 }  // namespace sagars
+
+#if defined(SAGARS_CUDA_EMU)
+#include "tc_emu.h"
+#endif

@@ -20,6 +20,13 @@
 
 namespace sagars {
 
+// "shared-window address" of a pointer into the block's dynamic shared memory: its offset in that buffer (what the matrix
+// descriptors of tc.cuh pack; the buffer is 1024-byte aligned, so 16-byte granules line up)
+inline uint32_t smem_u32(const void* p)
+{
+    return (uint32_t)(reinterpret_cast<uintptr_t>(p) - reinterpret_cast<uintptr_t>(::cuda_emu::dynamic_smem));
+}
+
 namespace emu_async {
 
 struct Piece { void* dst; const void* src; };

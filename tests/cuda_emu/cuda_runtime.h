@@ -109,8 +109,8 @@ template <class K, class... A>
 void launch2d(unsigned grid_x, unsigned grid_y, unsigned block, size_t smem_bytes, K kernel, A... args)
 {
     const unsigned grid = grid_x * grid_y;
-    std::vector<unsigned char> smem(smem_bytes + 32);
-    dynamic_smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem.data()) + 15u) & ~uintptr_t(15));
+    std::vector<unsigned char> smem(smem_bytes + 2048);
+    dynamic_smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem.data()) + 1023u) & ~uintptr_t(1023));
     std::vector<Warp> w((block + 31) / 32);
     warps = &w;
     blockDim = {block, 1, 1};

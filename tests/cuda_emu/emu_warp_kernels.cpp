@@ -6,6 +6,7 @@
 #include "render_backward_warp_kernels.cuh"
 #include "render_backward_kernels.cuh"
 #include "render_backward_mma_kernels.cuh"
+#include "render_forward_tc_kernels.cuh"
 #include "math.cuh"
 
 using namespace sagars;
@@ -79,4 +80,15 @@ extern "C" int emu_backward_tile(int kind, int md, int W, int H, int K, const ui
 #undef GO1
 #undef GO2
     return -1;
+}
+
+// the tcgen05 / TMEM tile forward (K = 32 only)
+extern "C" int emu_forward_tc(int W, int H, const uint2* ranges, const uint32_t* point_list, const float* geo, const float* features,
+                              const float* bg, float* final_T, uint32_t* n_contrib, float* out_color)
+{
+    cuda_emu::thread_exit_hook = emu_async::flush_thread;
+    const unsigned tx = (W + TILE_X - 1) / TILE_X, ty = (H + TILE_Y - 1) / TILE_Y;
+    cuda_emu::launch2d(tx, ty, TILE_PIX, sizeof(FwdTcSmem) + 1024, render_forward_tc_kernel, ranges, point_list, W, H, geo, features, bg,
+                       final_T, n_contrib, out_color);
+    return 0;
 }

@@ -41,6 +41,8 @@ def emu(request):
     L.emu_backward_warp.argtypes = [C.c_int] * 4 + [C.c_void_p] * 11
     L.emu_backward_tile.restype = C.c_int
     L.emu_backward_tile.argtypes = [C.c_int] * 5 + [C.c_void_p] * 11
+    L.emu_forward_tc.restype = C.c_int
+    L.emu_forward_tc.argtypes = [C.c_int] * 2 + [C.c_void_p] * 8
     L.emu_make_geo.argtypes = [C.c_int] + [C.c_void_p] * 3
     return L
 
@@ -90,6 +92,32 @@ def test_forward_warp_kernel(emu, case):
     n_contrib = np.zeros((H, W), np.uint32)
     color = np.zeros((K, H, W), np.float32)
     rc = emu.emu_forward_warp(W, H, K, _p(ranges), _p(pl), _p(geo), _p(feats), _p(bg), _p(final_T), _p(n_contrib), _p(color))
+    assert rc == 0
+    assert np.array_equal(n_contrib, fw.n_contrib)
+    np.testing.assert_allclose(final_T, fw.final_T, rtol=5e-6, atol=1e-9)
+    np.testing.assert_allclose(color, fw.color, rtol=5e-6, atol=5e-7)
+
+
+@pytest.mark.parametrize("case", [("k32", 300, 32, 48, 5.0), ("k32_ragged", 220, 27, 41, 4.0), ("k32_opaque", 260, 32, 32, 5.0), ("k32_sparse", 30, 48, 48, 2.0)],
+                         ids=lambda c: c[0])
+def test_forward_tcgen05_tile_kernel(emu, case):
+    """The opt-in tile-per-CTA forward on tcgen05 (SAGARS_FLAG_FWD_TILE; csrc/render_forward_tc_kernels.cuh): operand tiles in the
+    canonical K-major layout, asynchronous MMAs committed to mbarriers (executed by the shim as late as the model allows), TMEM
+    accumulators read back with tcgen05.ld."""
+    if emu.variant == "packed":
+        pytest.skip("the build variant only touches the warp-per-block kernels")
+    name, P, H, W, sigma = case
+    K = 32
+    sc = synthetic.scene(P, H, W, K, sigma_px=sigma)
+    if name == "k32_opaque":
+        sc.gauss.opacities = torch.full_like(sc.gauss.opacities, 0.9995)
+    bg = np.linspace(0.2, 0.8, K).astype(np.float32)
+    fw = _oracle_forward(sc, K, False, bg)
+    geo, feats, ranges, pl = _inputs(emu, fw, sc, K)
+    final_T = np.zeros((H, W), np.float32)
+    n_contrib = np.zeros((H, W), np.uint32)
+    color = np.zeros((K, H, W), np.float32)
+    rc = emu.emu_forward_tc(W, H, _p(ranges), _p(pl), _p(geo), _p(feats), _p(bg), _p(final_T), _p(n_contrib), _p(color))
     assert rc == 0
     assert np.array_equal(n_contrib, fw.n_contrib)
     np.testing.assert_allclose(final_T, fw.final_T, rtol=5e-6, atol=1e-9)
