@@ -30,9 +30,6 @@ struct BwSmem {
     float rowQ[BW_N][32];           // same layout; holds S during (2)
     float4 ctab[BW_TAB][2];         // candidate records (x, y, cx, cy | cz, opacity, accept_threshold, -), list order
     uint32_t cid[BW_TAB];           // their Gaussian ids
-#if !defined(SAGARS_PACK_CPOS)
-    int32_t cpos[BW_TAB];           // their positions in the tile's list
-#endif                                // SAGARS_PACK_CPOS: the position rides in the record's unused 8th float instead
 };
 
 // NQ : float4 groups covering the gradient channels (K colour channels [+ 1 mask channel when MD])
@@ -192,11 +189,7 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
             const float4 g1 = sm.ctab[gs + i][1];
             const float dx = g0.x - pixx, dy = g0.y - pixy;
             const float pw = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
-#if defined(SAGARS_PACK_CPOS)
             const bool cd = (__float_as_int(g1.w) < my_n) && !(pw > 0.0f) && (pw >= g1.z);
-#else
-            const bool cd = (sm.cpos[gs + i] < my_n) && !(pw > 0.0f) && (pw >= g1.z);
-#endif
             const int col = (lane + 4 * i) & 31;
             float w = 0.f, q = 0.f;
             if (cd) {
@@ -336,16 +329,10 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
         if (keep) {
             const int slot = ntab + __popc(km & lt);
             sm.ctab[slot][0] = r0_cur;
-#if defined(SAGARS_PACK_CPOS)
             float4 r1p = r1_cur;
             r1p.w = __int_as_float(pos_cur);
             sm.ctab[slot][1] = r1p;
             sm.cid[slot] = id_cur;
-#else
-            sm.ctab[slot][1] = r1_cur;
-            sm.cid[slot] = id_cur;
-            sm.cpos[slot] = pos_cur;
-#endif
         }
         ntab += __popc(km);
         float4 r0_nxt = make_float4(0.f, 0.f, 0.f, 0.f), r1_nxt = r0_nxt;
@@ -367,17 +354,9 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
             float4 a0, a1;
             uint32_t ci = 0;
             int cp = 0;
-#if defined(SAGARS_PACK_CPOS)
             if (lane < left) { a0 = sm.ctab[gs + lane][0]; a1 = sm.ctab[gs + lane][1]; ci = sm.cid[gs + lane]; }
-#else
-            if (lane < left) { a0 = sm.ctab[gs + lane][0]; a1 = sm.ctab[gs + lane][1]; ci = sm.cid[gs + lane]; cp = sm.cpos[gs + lane]; }
-#endif
             __syncwarp();
-#if defined(SAGARS_PACK_CPOS)
             if (lane < left) { sm.ctab[lane][0] = a0; sm.ctab[lane][1] = a1; sm.cid[lane] = ci; }
-#else
-            if (lane < left) { sm.ctab[lane][0] = a0; sm.ctab[lane][1] = a1; sm.cid[lane] = ci; sm.cpos[lane] = cp; }
-#endif
             __syncwarp();
         }
         ntab = (gs >= ntab) ? 0 : ntab - gs;

@@ -30,9 +30,6 @@ struct FwSmem {
     float F[FW_N][FwCfg<NQ>::RS];         // gathered feature rows (rotated, see FwCfg)
     float4 ctab[FW_TAB][2];               // candidate records (x, y, cx, cy | cz, opacity, accept_threshold, -), list order
     uint32_t cid[FW_TAB];                 // their Gaussian ids
-#if !defined(SAGARS_PACK_CPOS)
-    int32_t cpos[FW_TAB];                 // their positions in the tile's list
-#endif                                // SAGARS_PACK_CPOS: the position rides in the record's unused 8th float instead
 };
 
 // NQ : float4 groups covering the K colour channels;  VEC: K % 4 == 0 -> feature rows are read as float4
@@ -119,11 +116,7 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
                         } else {
                             w = alpha * T;
                             T = test_T;
-#if defined(SAGARS_PACK_CPOS)
                             last_contributor = (uint32_t)(__float_as_int(g1.w) + 1);
-#else
-                            last_contributor = (uint32_t)(sm.cpos[gs + i] + 1);
-#endif
                         }
                     }
                 }
@@ -188,16 +181,10 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
             if (keep) {
                 const int slot = ntab + __popc(km & lt);
                 sm.ctab[slot][0] = r0_cur;
-#if defined(SAGARS_PACK_CPOS)
                 float4 r1p = r1_cur;
                 r1p.w = __int_as_float(pos_cur);
                 sm.ctab[slot][1] = r1p;
                 sm.cid[slot] = id_cur;
-#else
-                sm.ctab[slot][1] = r1_cur;
-                sm.cid[slot] = id_cur;
-                sm.cpos[slot] = pos_cur;
-#endif
             }
             ntab += __popc(km);
             float4 r0_nxt = make_float4(0.f, 0.f, 0.f, 0.f), r1_nxt = r0_nxt;
@@ -219,17 +206,9 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
                 float4 a0, a1;
                 uint32_t ci = 0;
                 int cp = 0;
-#if defined(SAGARS_PACK_CPOS)
                 if (lane < left) { a0 = sm.ctab[gs + lane][0]; a1 = sm.ctab[gs + lane][1]; ci = sm.cid[gs + lane]; }
-#else
-                if (lane < left) { a0 = sm.ctab[gs + lane][0]; a1 = sm.ctab[gs + lane][1]; ci = sm.cid[gs + lane]; cp = sm.cpos[gs + lane]; }
-#endif
                 __syncwarp();
-#if defined(SAGARS_PACK_CPOS)
                 if (lane < left) { sm.ctab[lane][0] = a0; sm.ctab[lane][1] = a1; sm.cid[lane] = ci; }
-#else
-                if (lane < left) { sm.ctab[lane][0] = a0; sm.ctab[lane][1] = a1; sm.cid[lane] = ci; sm.cpos[lane] = cp; }
-#endif
                 __syncwarp();
             }
             ntab = (gs >= ntab) ? 0 : ntab - gs;

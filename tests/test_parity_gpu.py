@@ -294,11 +294,7 @@ def test_blend_kernel_variants_agree(cfg):
         assert ok, (key, report)
 
 
-EXPERIMENTAL = os.environ.get("SAGARS_TEST_EXPERIMENTAL") == "1"
 
-
-@pytest.mark.skipif(not EXPERIMENTAL, reason="opt-in variant not yet run on a GPU: set SAGARS_TEST_EXPERIMENTAL=1 (a wait that "
-                                             "never completes traps after ~2^26 polls instead of hanging)")
 @pytest.mark.parametrize("cfg", [("base", 4000, 90, 130, 3, False), ("depth", 4000, 90, 130, 3, True), ("k16", 2500, 80, 96, 16, False),
                                  ("k32", 3000, 72, 104, 32, False), ("k64", 1500, 64, 80, 64, False), ("k5", 1500, 64, 80, 5, False),
                                  ("long_lists", 6000, 48, 48, 8, False)],
@@ -322,7 +318,6 @@ def test_tma_staging_is_bit_identical(cfg):
             assert np.array_equal(x, y), f
 
 
-@pytest.mark.skipif(not EXPERIMENTAL, reason="added after the round's GPU budget was spent: set SAGARS_TEST_EXPERIMENTAL=1, un-gate once green")
 @pytest.mark.parametrize("mod", [0.6, 1.7])
 def test_scale_modifier_matches_oracle(mod):
     """scale_modifier != 1 (the viewer's scaling slider): forward state and every gradient against the CPU oracle, including the
@@ -355,7 +350,6 @@ def test_scale_modifier_matches_oracle(mod):
         assert r <= 1.0, f"{name}: max|d|={d:.3e} max|ref|={s_:.3e}"
 
 
-@pytest.mark.skipif(not EXPERIMENTAL, reason="opt-in variant not yet run on a GPU: set SAGARS_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("cfg", [("cf", 6000, 120, 168, 32, 2.0), ("base_ragged", 4000, 75, 101, 3, 2.0), ("one_tile", 300, 16, 16, 32, 2.0),
                                  ("mid_segments", 12000, 64, 64, 3, 14.0),      # tiles with 1024 < n <= 8192 instances
                                  ("huge_segments", 20000, 32, 48, 3, 60.0),     # tiles with more than 8192 instances

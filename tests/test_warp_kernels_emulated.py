@@ -23,13 +23,13 @@ from oracle import oracle as orc
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-# "packed": the opt-in build variant -DSAGARS_PACK_CPOS (a candidate's list position rides in the unused 8th float of its record
-# in the warp kernels' candidate tables; 61 -> 55 instructions in the forward's scalar loop, not yet run on a GPU)
-@pytest.fixture(scope="module", params=["default", "packed"])
+# (a candidate's list position rides in the unused 8th float of its record in the warp kernels' candidate tables: measured on
+# B200 in round 2, forward 1.009 -> 0.931 ms at c2, and made the only code path)
+@pytest.fixture(scope="module", params=["default"])
 def emu(request):
     d = tempfile.mkdtemp(prefix="sagars_emu_")
     so = os.path.join(d, "libemu_warp.so")
-    extra = ["-DSAGARS_PACK_CPOS"] if request.param == "packed" else []
+    extra = []
     subprocess.check_call(["g++", "-O1", "-std=c++20", "-pthread", "-ffp-contract=off", "-shared", "-fPIC"] + extra +
                           ["-I", os.path.join(ROOT, "tests", "cuda_emu"), "-I", os.path.join(ROOT, "seganygaussians_b200", "csrc"),
                            os.path.join(ROOT, "tests", "cuda_emu", "emu_warp_kernels.cpp"), "-o", so])

@@ -7,7 +7,7 @@ set -u
 mkdir -p gpurun_out
 N=${N:-2}
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
-echo "== gated multi-GPU tests =="; SAGARS_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_multi_gpu.py -m gpu -q 2>&1 | tail -8 | tee gpurun_out/r2_multi_gpu_tests.log
+echo "== gated multi-GPU tests =="; timeout 300 python -m pytest tests/test_multi_gpu.py -m gpu -q 2>&1 | tail -8 | tee gpurun_out/r2_multi_gpu_tests.log
 for variant in "" "--overlap-allreduce" "--allreduce multimem"; do
   tag=$(echo "${variant:-default}" | tr -d ' -')
   echo "== bench N=$N ${variant:-default} =="
