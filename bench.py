@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fwd-kernel", default="default", choices=["default", "tile", "warp_any"], help="developer A/B switch (rasterizer.set_blend_kernels)")
-    ap.add_argument("--bwd-kernel", default="default", choices=["default", "tile"], help="developer A/B switch")
+    ap.add_argument("--bwd-kernel", default="default", choices=["default", "tile", "tc"], help="developer A/B switch")
     ap.add_argument("--overlap-allreduce", action="store_true",
                     help="N > 1, developer switch: all-reduce on a side stream, gating only the next forward's blend stage "
                          "(its geometry stages overlap the exchange); default: the all-reduce serialises with the step")
@@ -340,7 +340,7 @@ def main():
                    "P_visible": radii_vis, "R_instances": R_inst,
                    "kernels": {"forward": {"default": "mma.sync warp kernel at K=32, fp32 tile kernel otherwise", "tile": "tcgen05 tile kernel",
                                            "warp_any": "mma.sync warp kernel for every K"}[a.fwd_kernel],
-                               "backward": "mma.sync warp kernel" if a.bwd_kernel == "default" else "mma.sync tile kernel",
+                               "backward": {"default": "mma.sync warp kernel", "tile": "mma.sync tile kernel", "tc": "tcgen05 / TMEM pixel-group kernel"}[a.bwd_kernel],
                                "binning": a.binning},
                    "S_pair_tests_upper_bound": S_pairs, "pairs_up_to_last_contributor": pairs_to_last},
         "e2e": {"value": e2e_value, "unit": "Gaussian*pixel/s", "ms_per_step": ms_e2e / a.steps,

@@ -82,6 +82,9 @@ enum {
                                         sorts its own segment (tile_sort.cu) instead of duplicate + 6 radix passes + range
                                         detection.  Bit-identical point_list / keys / ranges; opt-in until measured            */
 
+#define SAGARS_FLAG_BWD_TC 2048u     /* backward at C = 32 precomputed colours: tcgen05 / TMEM kernel, one CTA per 16x8 pixel group
+                                        (render_backward_tc.cu) instead of the mma.sync warp-per-block kernel                  */
+
 /* Allocator callback: return a device pointer to at least `bytes` bytes (256-B aligned), or NULL.
  * Replaces: std::function<char*(size_t)> geometryBuffer / binningBuffer / imageBuffer
  *           (CF cuda_rasterizer/rasterizer.h:33-35). */

@@ -436,6 +436,8 @@ int sagars_backward(const sagars_backward_args* a, void* stream_)
             ProfScope ps(ST_RENDER_BWD, s);
             if (a->flags & SAGARS_FLAG_NO_TENSOR_CORES) rc = launch_render_backward(*a, d, g, im, point_list, ggrad, s, debug);
             else if (a->flags & SAGARS_FLAG_BWD_TILE) rc = launch_render_backward_mma(*a, d, g, im, point_list, ggrad, s, debug);
+            else if ((a->flags & SAGARS_FLAG_BWD_TC) && !md && d.C == 32 && a->colors_precomp != nullptr)
+                rc = launch_render_backward_tc(*a, d, g, im, point_list, ggrad, s, debug);
             else rc = launch_render_backward_warp(*a, d, g, im, point_list, ggrad, s, debug);
         }
         if (rc) return rc;

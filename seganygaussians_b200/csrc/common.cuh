@@ -229,6 +229,8 @@ int launch_render_backward(const sagars_backward_args& a, const Dims& d, GeomVie
                            const uint32_t* point_list, float* ggrad, cudaStream_t s, bool debug);
 int launch_render_backward_warp(const sagars_backward_args& a, const Dims& d, GeomView g, ImageView im,
                                 const uint32_t* point_list, float* ggrad, cudaStream_t s, bool debug);
+int launch_render_backward_tc(const sagars_backward_args& a, const Dims& d, GeomView g, ImageView im,
+                              const uint32_t* point_list, float* ggrad, cudaStream_t s, bool debug);
 int launch_render_backward_mma(const sagars_backward_args& a, const Dims& d, GeomView g, ImageView im,
                                const uint32_t* point_list, float* ggrad, cudaStream_t s, bool debug);
 int launch_geom_backward(const sagars_backward_args& a, const Dims& d, GeomView g, const float* ggrad,

@@ -7,10 +7,12 @@
 #include "candidate.cuh"
 
 // the operand tiles of tcgen05.mma want generous alignment: this kernel asks for 1024 bytes (the CPU shim aligns its buffer likewise)
+#ifndef SAGARS_DYNAMIC_SMEM_1024
 #if defined(SAGARS_CUDA_EMU)
 #define SAGARS_DYNAMIC_SMEM_1024(name) SAGARS_DYNAMIC_SMEM(name)
 #else
 #define SAGARS_DYNAMIC_SMEM_1024(name) extern __shared__ __align__(1024) unsigned char name[]
+#endif
 #endif
 
 namespace sagars {

@@ -134,6 +134,8 @@ def _flags(settings: GaussianRasterizationSettings, extra: int = 0) -> int:
         f |= _lib.FLAG_FWD_WARP_ANY
     if _BACKWARD_KERNEL == "tile":
         f |= _lib.FLAG_BWD_TILE
+    elif _BACKWARD_KERNEL == "tc":
+        f |= _lib.FLAG_BWD_TC
     if _STAGING == "tma":
         f |= _lib.FLAG_STAGE_TMA
     if _BINNING == "tile_sort":
@@ -145,7 +147,8 @@ _USE_CUB_SORT = False
 _USE_TENSOR_CORES = True
 _FORWARD_KERNEL = "default"    # "default": mma.sync warp kernel at K = 32, fp32 SIMT otherwise; "tile": tcgen05 tile kernel at
                                # K = 32; "warp_any": the warp kernel for every colour-only channel count
-_BACKWARD_KERNEL = "default"   # "default": one warp per 8x4 pixel block; "tile": one CTA per 16x16 tile
+_BACKWARD_KERNEL = "default"   # "default": one warp per 8x4 pixel block (mma.sync); "tile": one CTA per 16x16 tile (mma.sync);
+                               # "tc": tcgen05 / TMEM kernel, one CTA per 16x8 pixel group (C = 32 precomputed colours)
 _STAGING = "cp_async"          # how the tile-per-CTA fp32 forward gathers a batch into shared memory: "cp_async" (16-byte LDGSTS
                                # pieces) or "tma" (one cp.async.bulk per row completing on an mbarrier; opt-in until measured)
 _BINNING = "radix"             # "radix": duplicate keys + global LSD radix sort + range detection; "tile_sort": per-tile counts ->
@@ -175,8 +178,8 @@ def set_tensor_cores(enabled: bool) -> None:
 def set_blend_kernels(forward: str = "default", backward: str = "default") -> None:
     """Select between the tensor-core blend kernel variants (all give the same results to fp32 rounding)."""
     global _FORWARD_KERNEL, _BACKWARD_KERNEL
-    if forward not in ("default", "tile", "warp_any") or backward not in ("default", "tile"):
-        raise ValueError("forward in {'default', 'tile', 'warp_any'}, backward in {'default', 'tile'}")
+    if forward not in ("default", "tile", "warp_any") or backward not in ("default", "tile", "tc"):
+        raise ValueError("forward in {'default', 'tile', 'warp_any'}, backward in {'default', 'tile', 'tc'}")
     _FORWARD_KERNEL, _BACKWARD_KERNEL = forward, backward
 
 

@@ -7,6 +7,7 @@
 #include "render_backward_kernels.cuh"
 #include "render_backward_mma_kernels.cuh"
 #include "render_forward_tc_kernels.cuh"
+#include "render_backward_tc_kernels.cuh"
 #include "math.cuh"
 
 using namespace sagars;
@@ -90,5 +91,17 @@ extern "C" int emu_forward_tc(int W, int H, const uint2* ranges, const uint32_t*
     const unsigned tx = (W + TILE_X - 1) / TILE_X, ty = (H + TILE_Y - 1) / TILE_Y;
     cuda_emu::launch2d(tx, ty, TILE_PIX, sizeof(FwdTcSmem) + 1024, render_forward_tc_kernel, ranges, point_list, W, H, geo, features, bg,
                        final_T, n_contrib, out_color);
+    return 0;
+}
+
+// the tcgen05 / TMEM backward (C = 32 precomputed colours): one CTA per 16x8 pixel group
+extern "C" int emu_backward_tc(int W, int H, const uint2* ranges, const uint32_t* point_list, const float* bg, const float* geo,
+                               const float* features, const float* final_T, const uint32_t* n_contrib, const float* dL_dpix,
+                               float* ggrad, float* dL_dcolors)
+{
+    cuda_emu::thread_exit_hook = emu_async::flush_thread;
+    const unsigned tx = (W + TILE_X - 1) / TILE_X, ty = (H + TILE_Y - 1) / TILE_Y;
+    cuda_emu::launch2d(tx, 2 * ty, BT_PIX, sizeof(BtSmem<16>) + 1024, render_backward_tc_kernel<16>, ranges, point_list, W, H, bg, geo, features,
+                       final_T, n_contrib, dL_dpix, ggrad, dL_dcolors);
     return 0;
 }

@@ -33,8 +33,9 @@ inline float tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE
 inline void execute(const Mma& m)
 {
     const int N = (int)((m.idesc >> 17) & 0x3F) << 3, M = (int)((m.idesc >> 24) & 0x1F) << 4;
-    if (((m.idesc >> 15) & 1u) || ((m.idesc >> 16) & 1u) || M != 128) {
-        std::fprintf(stderr, "[cuda_emu] tcgen05.mma: only K-major operands with M = 128 are modelled\n");
+    const bool a_mn = ((m.idesc >> 15) & 1u) != 0;
+    if (((m.idesc >> 16) & 1u) || M != 128) {
+        std::fprintf(stderr, "[cuda_emu] tcgen05.mma: only a K-major B operand and M = 128 are modelled\n");
         std::abort();
     }
     auto field = [](uint64_t d, int sh) { return (size_t)((d >> sh) & 0x3FFF) << 4; };
@@ -46,11 +47,18 @@ inline void execute(const Mma& m)
         std::memcpy(&v, base + start + (size_t)(k / 4) * lbo + (size_t)(r / 8) * sbo + (size_t)(r % 8) * 16 + (size_t)(k % 4) * 4, 4);
         return (double)tf32(v);
     };
+    // MN-major operand (tc.cuh): element (row, k) at (k/8)*LBO + (row/4)*SBO + (k%8)*16 + (row%4)*4; rows may alias other data
+    // (the caller then ignores their accumulator rows): read as raw bits, NaN / Inf stay confined to their own row
+    auto elem_mn = [&](size_t start, size_t lbo, size_t sbo, int r, int k) {
+        float v;
+        std::memcpy(&v, base + start + (size_t)(k / 8) * lbo + (size_t)(r / 4) * sbo + (size_t)(k % 8) * 16 + (size_t)(r % 4) * 4, 4);
+        return (double)tf32(v);
+    };
     const int lane0 = (int)(m.tmem_d >> 16), col0 = (int)(m.tmem_d & 0xFFFF);
     for (int r = 0; r < M; r++)
         for (int n = 0; n < N; n++) {
             double acc = m.accumulate ? (double)tmem[lane0 + r][col0 + n] : 0.0;
-            for (int k = 0; k < 8; k++) acc += elem(a0, a_lbo, a_sbo, r, k) * elem(b0, b_lbo, b_sbo, n, k);
+            for (int k = 0; k < 8; k++) acc += (a_mn ? elem_mn(a0, a_lbo, a_sbo, r, k) : elem(a0, a_lbo, a_sbo, r, k)) * elem(b0, b_lbo, b_sbo, n, k);
             tmem[lane0 + r][col0 + n] = (float)acc;
         }
 }
@@ -129,6 +137,11 @@ inline void tmem_ld32(uint32_t taddr, float* v)
 {
     const int lane = (int)(taddr >> 16) + (int)(threadIdx.x & 31), col = (int)(taddr & 0xFFFF);
     for (int i = 0; i < 32; i++) v[i] = emu::tmem[lane][col + i];
+}
+inline void tmem_ld16(uint32_t taddr, float* v)
+{
+    const int lane = (int)(taddr >> 16) + (int)(threadIdx.x & 31), col = (int)(taddr & 0xFFFF);
+    for (int i = 0; i < 16; i++) v[i] = emu::tmem[lane][col + i];
 }
 inline void bar_sync_128(int id) { emu::named[id & 15].sync(128); }
 

@@ -276,7 +276,7 @@ def test_speculative_binning_matches_exact_layout():
                          ids=lambda c: c[0])
 def test_blend_kernel_variants_agree(cfg):
     """Every shipped blend-kernel variant (forward: mma.sync warp / tcgen05 tile / fp32 SIMT; backward: warp-per-block /
-    CTA-per-tile / fp32 SIMT) gives the same integer state and the same fp32 results within the parity tolerance."""
+    CTA-per-tile / tcgen05 pixel-group / fp32 SIMT) gives the same integer state and the same fp32 results within the parity tolerance."""
     from seganygaussians_b200 import rasterizer as R
     name, P, H, W, K, depth = cfg
     sc = synthetic.scene(P, H, W, K)
@@ -284,7 +284,7 @@ def test_blend_kernel_variants_agree(cfg):
         base = common.run_torch_impl("ours", sc, K, depth=depth, tensor_cores=False)       # fp32 SIMT forward + backward
         runs = {}
         for fwd in ("default", "tile", "warp_any"):
-            for bwd in ("default", "tile"):
+            for bwd in ("default", "tile", "tc"):            # "tc" falls back to the default kernel unless C = 32 precomputed colours
                 R.set_blend_kernels(forward=fwd, backward=bwd)
                 runs[(fwd, bwd)] = common.run_torch_impl("ours", sc, K, depth=depth, tensor_cores=True)
     finally:

@@ -41,6 +41,8 @@ def emu(request):
     L.emu_backward_warp.argtypes = [C.c_int] * 4 + [C.c_void_p] * 11
     L.emu_backward_tile.restype = C.c_int
     L.emu_backward_tile.argtypes = [C.c_int] * 5 + [C.c_void_p] * 11
+    L.emu_backward_tc.restype = C.c_int
+    L.emu_backward_tc.argtypes = [C.c_int] * 2 + [C.c_void_p] * 10
     L.emu_forward_tc.restype = C.c_int
     L.emu_forward_tc.argtypes = [C.c_int] * 2 + [C.c_void_p] * 8
     L.emu_make_geo.argtypes = [C.c_int] + [C.c_void_p] * 3
@@ -128,7 +130,7 @@ def test_forward_tcgen05_tile_kernel(emu, case):
                                   ("k32_opaque", 160, 24, 32, 32, False, 4.0, True),       # alpha hits the 0.99 clamp, pixels saturate early
                                   ("k3", 300, 32, 32, 3, False, 5.0, False), ("depth_mask", 300, 32, 32, 3, True, 5.0, True)],
                          ids=lambda c: c[0])
-@pytest.mark.parametrize("kind", ["warp", "simt_tile", "mma_tile"])
+@pytest.mark.parametrize("kind", ["warp", "simt_tile", "mma_tile", "tcgen05"])
 def test_backward_kernels(emu, case, kind):
     """kind: the default warp-per-block kernel, and the two CTA-per-tile alternates (fp32 SIMT behind
     SAGARS_FLAG_NO_TENSOR_CORES -- csrc/render_backward_kernels.cuh; mma.sync behind SAGARS_FLAG_BWD_TILE --
@@ -149,7 +151,11 @@ def test_backward_kernels(emu, case, kind):
     dcol = np.zeros((P, K), np.float32)
     final_T = np.ascontiguousarray(fw.final_T.astype(np.float32))
     n_contrib = np.ascontiguousarray(fw.n_contrib.astype(np.uint32))
-    if kind == "warp":
+    if kind == "tcgen05":
+        if K != 32 or depth:
+            pytest.skip("the tcgen05 backward handles C = 32 precomputed colours")
+        rc = emu.emu_backward_tc(W, H, _p(ranges), _p(pl), _p(bg), _p(geo), _p(feats), _p(final_T), _p(n_contrib), _p(dpix), _p(ggrad), _p(dcol))
+    elif kind == "warp":
         rc = emu.emu_backward_warp(int(depth), W, H, K, _p(ranges), _p(pl), _p(bg), _p(geo), _p(feats), _p(final_T), _p(n_contrib),
                                    _p(dpix), _p(dmask), _p(ggrad), _p(dcol))
     else:

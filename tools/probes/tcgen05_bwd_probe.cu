@@ -54,8 +54,14 @@ constexpr int F_LBO = 256, F_BYTES = 8 * F_LBO;        // per hi / lo
 
 __global__ void __launch_bounds__(128) probe(const float* __restrict__ G, const float* __restrict__ X, const float* __restrict__ F,
                                              const float* __restrict__ WQ, float* __restrict__ S_out, float* __restrict__ D_out,
-                                             int* __restrict__ status, long long* __restrict__ cyc, int reps)
+                                             int* __restrict__ status, long long* __restrict__ cyc, int reps, int variant)
 {
+    // variant 0: as designed (A3 = the G tile read MN-major, overlapping row chunks, NaN slack)
+    //         1: same, slack zeroed            2: A3 = a separate K-major copy [px/4][row/8][row%8][4]  (rows 0..71 valid, rest zero)
+    //         3: MN-major, LBO / SBO swapped   4: MN-major, M = 64 instruction (rows 0..63 only)
+    //         5: MN-major from a dense copy [px/8][32 chunks][px%8][4] (no overlap)
+    //         6: TRANSPOSED product: D'[128 x 80] = A = the w/q tile (K-major, rows 64..127 alias) x B = the G tile read MN-major (N = 80)
+    //         7: as 6 with the dense copy of variant 5 as B
     extern __shared__ __align__(1024) unsigned char smem[];
     float* Gt = reinterpret_cast<float*>(smem);
     float* B3 = reinterpret_cast<float*>(smem + G_BYTES);
@@ -63,6 +69,7 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ G, const 
     float* Fl = reinterpret_cast<float*>(smem + G_BYTES + B3_BYTES + F_BYTES);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + G_BYTES + B3_BYTES + 2 * F_BYTES);
     uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 2);
+    float* A3 = reinterpret_cast<float*>(smem + G_BYTES + B3_BYTES + 2 * F_BYTES + 64);   // 64 KB: K-major or dense MN-major copy
     const int tid = threadIdx.x, warp = tid >> 5;
 
     // G tile: thread = pixel
@@ -78,7 +85,14 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ G, const 
         }
         *reinterpret_cast<float4*>(base + 16 * 32) = make_float4(X[tid * 8 + 0], X[tid * 8 + 1], X[tid * 8 + 2], X[tid * 8 + 3]);
         *reinterpret_cast<float4*>(base + 17 * 32) = make_float4(X[tid * 8 + 4], X[tid * 8 + 5], X[tid * 8 + 6], X[tid * 8 + 7]);
-        for (int i = tid; i < 14 * 32; i += 128) Gt[(NPX / 8) * (G_PG / 4) + i] = __int_as_float(0x7fc00000);   // slack = NaN on purpose
+        for (int i = tid; i < 14 * 32; i += 128) Gt[(NPX / 8) * (G_PG / 4) + i] = (variant == 0) ? __int_as_float(0x7fc00000) : 0.f;
+        for (int i = tid; i < 16384; i += 128) A3[i] = 0.f;
+        __syncthreads();
+        for (int row = 0; row < 72; row++) {        // value of A3 row `row` at pixel tid
+            const float v = Gt[(tid >> 3) * (G_PG / 4) + (row >> 2) * 32 + (tid & 7) * 4 + (row & 3)];
+            if (variant == 2) A3[(tid >> 2) * 512 + (row >> 3) * 32 + (row & 7) * 4 + (tid & 3)] = v;          // K-major, LBO = 2048, SBO = 128
+            else A3[(tid >> 3) * 1024 + (row >> 2) * 32 + (tid & 7) * 4 + (row & 3)] = v;                       // dense MN-major, LBO = 4096, SBO = 128
+        }
     }
     // F tile: thread t -> cand = t % 16, quad = t / 16
     {
@@ -120,7 +134,7 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ G, const 
     const uint32_t tS = tmem, tD = tmem + 64;
 
     constexpr uint32_t ID1 = idesc_tf32(128, NB, 0, 0);          // A K-major, B K-major
-    constexpr uint32_t ID3 = idesc_tf32(128, 4 * NB, 1, 0);      // A MN-major, B K-major
+    const uint32_t ID3 = (variant >= 6) ? idesc_tf32(128, 80, 0, 1) : idesc_tf32(variant == 4 ? 64 : 128, 4 * NB, variant == 2 ? 0 : 1, 0);
     bool ok = true;
     long long c1 = 0, c3 = 0;
     for (int r = 0; r < reps && ok; r++) {
@@ -142,8 +156,20 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ G, const 
         long long t1 = clock64();
         if (tid == 0) {
             const uint32_t g0 = smem_u32(Gt), b0 = smem_u32(B3);
-            for (int ks = 0; ks < NPX / 8; ks++)
-                mma_tf32(tD, make_desc(g0 + ks * G_PG, G_PG, 128), make_desc(b0 + ks * 2 * B3_LBO, B3_LBO, 128), ID3, ks > 0 ? 1u : 0u);
+            const uint32_t a3 = smem_u32(A3);
+            for (int ks = 0; ks < NPX / 8; ks++) {
+                uint64_t da;
+                if (variant >= 6) {
+                    const uint64_t db = (variant == 6) ? make_desc(g0 + ks * G_PG, G_PG, 128) : make_desc(a3 + ks * 4096, 4096, 128);
+                    mma_tf32(tS + 32, make_desc(b0 + ks * 2 * B3_LBO, B3_LBO, 128), db, ID3, ks > 0 ? 1u : 0u);
+                    continue;
+                }
+                if (variant == 2) da = make_desc(a3 + ks * 2 * 2048, 2048, 128);
+                else if (variant == 3) da = make_desc(g0 + ks * G_PG, 128, G_PG);
+                else if (variant == 5) da = make_desc(a3 + ks * 4096, 4096, 128);
+                else da = make_desc(g0 + ks * G_PG, G_PG, 128);
+                mma_tf32(tD, da, make_desc(b0 + ks * 2 * B3_LBO, B3_LBO, 128), ID3, ks > 0 ? 1u : 0u);
+            }
             commit(&bar[1]);
         }
         ok = ok && mbar_wait(&bar[1], r & 1, 20000000);
@@ -161,13 +187,16 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ G, const 
                      : "r"(tS + lane_base));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         for (int n = 0; n < 16; n++) S_out[tid * 16 + n] = __uint_as_float(v[n]);
-        for (int c = 0; c < 4; c++) {
+        const int ncol16 = (variant >= 6) ? 5 : 4;
+        const uint32_t tRead = (variant >= 6) ? tS + 32 : tD;
+        const int ostride = (variant >= 6) ? 80 : 64;
+        for (int c = 0; c < ncol16; c++) {
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
                            "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                         : "r"(tD + lane_base + 16 * c));
+                         : "r"(tRead + lane_base + 16 * c));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            for (int n = 0; n < 16; n++) D_out[tid * 64 + 16 * c + n] = __uint_as_float(v[n]);
+            for (int n = 0; n < 16; n++) D_out[tid * ostride + 16 * c + n] = __uint_as_float(v[n]);
         }
         if (tid == 0) { status[0] = 0; cyc[0] = c1; cyc[1] = c3; }
     }
@@ -190,25 +219,39 @@ int main()
     for (int i = 0; i < NPX * 2 * NB; i++) WQ[i] = (rand() / (float)RAND_MAX - 0.3f);
     float *dG, *dX, *dF, *dWQ, *dS, *dD; int* dSt; long long* dC;
     cudaMalloc(&dG, NPX * NCH * 4); cudaMalloc(&dX, NPX * 8 * 4); cudaMalloc(&dF, NB * NCH * 4); cudaMalloc(&dWQ, NPX * 2 * NB * 4);
-    cudaMalloc(&dS, NPX * 16 * 4); cudaMalloc(&dD, NPX * 64 * 4); cudaMalloc(&dSt, 4); cudaMalloc(&dC, 16);
+    cudaMalloc(&dS, NPX * 16 * 4); cudaMalloc(&dD, NPX * 80 * 4); cudaMalloc(&dSt, 4); cudaMalloc(&dC, 16);
     cudaMemcpy(dG, G, NPX * NCH * 4, cudaMemcpyHostToDevice); cudaMemcpy(dX, X, NPX * 8 * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(dF, F, NB * NCH * 4, cudaMemcpyHostToDevice); cudaMemcpy(dWQ, WQ, NPX * 2 * NB * 4, cudaMemcpyHostToDevice);
-    const int smem = G_BYTES + B3_BYTES + 2 * F_BYTES + 64;
+    const int smem = G_BYTES + B3_BYTES + 2 * F_BYTES + 64 + 65536;
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    for (int reps : {1, 2000}) {
+    for (int variant = 0; variant < 8; variant++)
+    for (int reps : {1, 500}) {
         int st = -1; cudaMemcpy(dSt, &st, 4, cudaMemcpyHostToDevice);
-        cudaMemset(dS, 0, NPX * 16 * 4); cudaMemset(dD, 0, NPX * 64 * 4);
-        probe<<<1, 128, smem>>>(dG, dX, dF, dWQ, dS, dD, dSt, dC, reps);
+        cudaMemset(dS, 0, NPX * 16 * 4); cudaMemset(dD, 0, NPX * 80 * 4);
+        probe<<<1, 128, smem>>>(dG, dX, dF, dWQ, dS, dD, dSt, dC, reps, variant);
         cudaError_t e = cudaDeviceSynchronize();
-        float* S = new float[NPX * 16]; float* D = new float[NPX * 64]; long long cyc[2] = {0, 0};
+        float* S = new float[NPX * 16]; float* D = new float[NPX * 80]; long long cyc[2] = {0, 0};
         cudaMemcpy(&st, dSt, 4, cudaMemcpyDeviceToHost); cudaMemcpy(S, dS, NPX * 16 * 4, cudaMemcpyDeviceToHost);
-        cudaMemcpy(D, dD, NPX * 64 * 4, cudaMemcpyDeviceToHost); cudaMemcpy(cyc, dC, 16, cudaMemcpyDeviceToHost);
+        cudaMemcpy(D, dD, NPX * 80 * 4, cudaMemcpyDeviceToHost); cudaMemcpy(cyc, dC, 16, cudaMemcpyDeviceToHost);
         double e1 = 0, m1 = 0, e3 = 0, m3 = 0, e3x = 0, m3x = 0;
         for (int p = 0; p < NPX; p++) for (int j = 0; j < NB; j++) {
             double s = 0; for (int c = 0; c < NCH; c++) s += (double)G[p * NCH + c] * F[j * NCH + c];
             e1 = fmax(e1, fabs(S[p * 16 + j] - s)); m1 = fmax(m1, fabs(s));
         }
         // rows 0..31 (+32..63): sum over columns (W_hi + W_lo) of both row groups = sum_p g[p][ch] w[p][j]; rows 64..69: columns Q
+        if (variant >= 6) {
+            // D'[row n][col m]: n = j (w_hi), 16 + j (w_lo), 32 + j (q_hi), 48 + j (q_lo); m = ch (hi), 32 + ch (lo), 64.. basis
+            for (int ch = 0; ch < NCH; ch++) for (int j = 0; j < NB; j++) {
+                double s = 0; for (int p = 0; p < NPX; p++) s += (double)G[p * NCH + ch] * WQ[p * 2 * NB + j];
+                const double got = (double)D[j * 80 + ch] + D[j * 80 + 32 + ch] + D[(16 + j) * 80 + ch] + D[(16 + j) * 80 + 32 + ch];
+                e3 = fmax(e3, fabs(got - s)); m3 = fmax(m3, fabs(s));
+            }
+            for (int m = 0; m < 6; m++) for (int j = 0; j < NB; j++) {
+                double s = 0; for (int p = 0; p < NPX; p++) s += (double)X[p * 8 + m] * WQ[p * 2 * NB + NB + j];
+                const double got = (double)D[(32 + j) * 80 + 64 + m] + D[(48 + j) * 80 + 64 + m];
+                e3x = fmax(e3x, fabs(got - s) / fmax(1.0, fabs(s))); m3x = fmax(m3x, fabs(s));
+            }
+        } else {
         for (int ch = 0; ch < NCH; ch++) for (int j = 0; j < NB; j++) {
             double s = 0; for (int p = 0; p < NPX; p++) s += (double)G[p * NCH + ch] * WQ[p * 2 * NB + j];
             const double got = (double)D[ch * 64 + j] + D[ch * 64 + 16 + j] + D[(32 + ch) * 64 + j] + D[(32 + ch) * 64 + 16 + j];
@@ -219,12 +262,17 @@ int main()
             const double got = (double)D[(64 + m) * 64 + 32 + j] + D[(64 + m) * 64 + 48 + j];
             e3x = fmax(e3x, fabs(got - s) / fmax(1.0, fabs(s))); m3x = fmax(m3x, fabs(s));
         }
+        }
         const bool good = e == cudaSuccess && st == 0 && e1 < 2e-5 * m1 && e3 < 2e-5 * m3 && e3x < 2e-5;
-        printf("reps=%d cuda=%s status=%d | GEMM1 rel err %.2e | GEMM3 colour rel err %.2e, moments rel err %.2e | cycles: GEMM1 %.0f GEMM3 %.0f | %s\n",
-               reps, cudaGetErrorString(e), st, e1 / m1, e3 / m3, e3x, (double)cyc[0] / reps, (double)cyc[1] / reps, good ? "BWD LAYOUTS OK" : "BWD LAYOUTS WRONG");
+        printf("variant=%d reps=%d cuda=%s status=%d | GEMM1 rel err %.2e | GEMM3 colour rel err %.2e, moments rel err %.2e | cycles: GEMM1 %.0f GEMM3 %.0f | %s\n",
+               variant, reps, cudaGetErrorString(e), st, e1 / m1, e3 / m3, e3x, (double)cyc[0] / reps, (double)cyc[1] / reps, good ? "BWD LAYOUTS OK" : "BWD LAYOUTS WRONG");
         if (!good) {
             printf(" S[0][0..3] %g %g %g %g\n", S[0], S[1], S[2], S[3]);
             printf(" D[0][0..3] %g %g %g %g | D[64][32..35] %g %g %g %g\n", D[0], D[1], D[2], D[3], D[64 * 64 + 32], D[64 * 64 + 33], D[64 * 64 + 34], D[64 * 64 + 35]);
+            double want0 = 0; for (int p2 = 0; p2 < NPX; p2++) want0 += (double)G[p2 * NCH + 0] * WQ[p2 * 2 * NB + 0];
+            printf(" expected colour[0][0] %g (sum of the four D entries %g); nonzero D entries:", want0, (double)D[0] + D[16] + D[32 * 64] + D[32 * 64 + 16]);
+            int nz = 0; for (int i = 0; i < NPX * 64; i++) if (D[i] != 0.f) nz++;
+            printf(" %d of %d\n", nz, NPX * 64);
         }
     }
     return 0;
