@@ -5,17 +5,21 @@
 
 * workload (config.workload): BASELINE.json configs[1] = synthetic 1M Gaussians, 1080x1920, K=32, one
   camera per GPU per step (SYN(P,H,W,K,cam) of BASELINE.md section 2.2; camera index = rank).
-* a "step" = one forward + backward of the rasterizer over one camera on every rank, plus (N>1) ONE NCCL
-  all-reduce of the per-Gaussian feature gradient dL_dcolors [P,K].  Weak scaling: per-GPU work is fixed.
+* a "step" = one forward + backward of the rasterizer over one camera on every rank, plus (N>1) ONE all-reduce of the
+  per-Gaussian feature gradient dL_dcolors [P,K].  Weak scaling: per-GPU work is fixed.
 * metric = Gaussians*pixels/s = (sum over ranks of P*H*W) * K_steps / time; time = CUDA events on the launching
   stream, barrier + synchronize on both sides, max over ranks.
-* `value`  : Gaussian parameters, upstream gradient and camera resident in HBM, operator called directly.
+* `value`  : Gaussian parameters, upstream gradient and camera resident in HBM, operator called directly; nothing but the
+             steps (and three NVML clock samples taken while the GPU is busy) runs between the two events.
 * `e2e`    : the same step through the reference-shaped public API as a user drives it -- per step the camera
              (view / projection / centre / background: the only host-side inputs the reference API has; the
              Gaussian parameters are resident model state exactly as in train_contrastive_feature.py) is copied
              from pinned host memory, the loss (sum(image * dL)) is read back to the host.
-* `roofline`: HBM roofline of the dominant kernel, from per-stage CUDA-event timings taken by the library on its
-             launch stream inside the timed region, with algorithmic bytes per launch as defined in DESIGN.md.
+* `roofline`: HBM roofline of the dominant kernel.  Its average launch duration comes from per-stage CUDA-event timings
+             taken by the library on its launch stream in a SEPARATE pass of the same steps (the instrumentation costs
+             ~18 event records per step, so it stays out of the `value` region); algorithmic bytes per launch as in DESIGN.md.
+* `c4`     : BASELINE.json configs[3] (3M Gaussians, 8 cameras, STRONG scaling: 8 / N cameras per rank, one all-reduce of
+             the 384 MB feature gradient per 8-camera batch), measured in the same run after the headline numbers.
 * `cpu_baseline`: the CPU oracle port (oracle/sagars_oracle.c, OpenMP over tiles) timed on the host cores on the
              same workload (rank 0, N=1 only).
 * `--impl reference`: the UNMODIFIED reference extension (oracle/_ref, rebuilt for sm_100a from /root/reference by
@@ -39,42 +43,48 @@ import torch
 
 WORKLOADS = {
     # BASELINE.json configs[1]
-    "c2": dict(P=1_000_000, H=1080, W=1920, K=32, desc="synthetic 1M Gaussians, 1080x1920, K=32 affinity features, 1 camera/GPU, fwd+bwd"),
+    "c2": dict(P=1_000_000, H=1080, W=1920, K=32, cameras=None,
+               desc="synthetic 1M Gaussians, 1080x1920, K=32 affinity features, 1 camera/GPU, fwd+bwd"),
+    # BASELINE.json configs[3]: strong scaling of an 8-camera batch
+    "c4": dict(P=3_000_000, H=1080, W=1920, K=32, cameras=8,
+               desc="synthetic 3M Gaussians, 1080x1920, K=32, batch of 8 cameras sharded over the GPUs, fwd+bwd + feature-gradient all-reduce"),
     # BASELINE.json configs[2]-like (parity-test case, not the bench line): 5M Gaussians
-    "c3": dict(P=5_000_000, H=1036, W=1600, K=32, desc="synthetic 5M Gaussians, 1036x1600, K=32 (garden-like), 1 camera/GPU, fwd+bwd"),
+    "c3": dict(P=5_000_000, H=1036, W=1600, K=32, cameras=None,
+               desc="synthetic 5M Gaussians, 1036x1600, K=32 (garden-like), 1 camera/GPU, fwd+bwd"),
     # configs[1] at K=3 (the BASE variant's channel count; developer A/B of the forward kernels, never a bench line)
-    "c2_k3": dict(P=1_000_000, H=1080, W=1920, K=3, desc="synthetic 1M Gaussians, 1080x1920, K=3, 1 camera/GPU, fwd+bwd"),
+    "c2_k3": dict(P=1_000_000, H=1080, W=1920, K=3, cameras=None, desc="synthetic 1M Gaussians, 1080x1920, K=3, 1 camera/GPU, fwd+bwd"),
     # small variant for quick local checks (never a bench line)
-    "tiny": dict(P=20_000, H=270, W=480, K=32, desc="tiny smoke workload"),
+    "tiny": dict(P=20_000, H=270, W=480, K=32, cameras=None, desc="tiny smoke workload"),
 }
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the BASELINE configs[3] strong-scaling leg")
     ap.add_argument("--fwd-kernel", default="default", choices=["default", "tile", "warp_any"], help="developer A/B switch (rasterizer.set_blend_kernels)")
-    ap.add_argument("--bwd-kernel", default="default", choices=["default", "tile", "tc"], help="developer A/B switch")
-    ap.add_argument("--overlap-allreduce", action="store_true",
-                    help="N > 1, developer switch: all-reduce on a side stream, gating only the next forward's blend stage "
-                         "(its geometry stages overlap the exchange); default: the all-reduce serialises with the step")
+    ap.add_argument("--bwd-kernel", default="default", choices=["default", "warp", "tile", "tc"], help="developer A/B switch")
+    ap.add_argument("--allreduce-mode", default="overlap", choices=["overlap", "sync"],
+                    help="N > 1: 'overlap' = the all-reduce runs on a side stream and gates only the next forward's blend stage (its "
+                         "geometry stages overlap the exchange); 'sync' = the all-reduce serialises with the step")
     ap.add_argument("--allreduce", default="nccl", choices=["nccl", "multimem"],
                     help="N > 1, developer switch: 'multimem' = the library's own all-reduce over the NVSwitch multicast mapping")
-    ap.add_argument("--binning", default="radix", choices=["radix", "tile_sort"], help="developer A/B switch (rasterizer.set_binning)")
+    ap.add_argument("--binning", default="default", choices=["default", "radix", "tile_sort", "depth_first"], help="developer A/B switch (rasterizer.set_binning)")
     return ap.parse_args()
 
 
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region, read through NVML (the quantities
     `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` prints; B200_PROFILING.md recipe).
-    Samples are taken explicitly from the launching thread while the GPU is busy with the timed steps (after
-    the launches of the middle step and of the last step, before the closing synchronise).  A polling child /
-    thread is deliberately NOT used: `nvidia-smi -lms 50` was measured to slow this launch-heavy step 3x and a
-    100 ms NVML thread still added up to ~1 ms/step of jitter, which would falsify the number it guards."""
+    Samples are taken explicitly from the launching thread at 25 / 50 / 75 % of the timed steps: the launching thread runs
+    several steps ahead of the GPU, so the GPU is busy with queued steps while NVML is read and the read costs no GPU time.
+    A polling child / thread is deliberately NOT used: `nvidia-smi -lms 50` was measured to slow this launch-heavy step 3x
+    and a 100 ms NVML thread still added up to ~1 ms/step of jitter, which would falsify the number it guards."""
 
     def __init__(self, index: int):
         self.index, self.rows, self.ok = index, [], False
@@ -128,6 +138,7 @@ def load_peaks():
 
 def algorithmic_bytes(P, R, HW, T, C):
     """DESIGN.md section 'algorithmic bytes' (SURVEY.md Appendix C): each datum crosses HBM once."""
+    binning = P * 20 + R * 12 + R * 24 + R * 8 + T * 8          # key emission + one sort's worth of traffic + range detection
     per_stage = {
         "preprocess": P * (44 + 60),
         "scan_block_sums": P * 8,
@@ -138,7 +149,154 @@ def algorithmic_bytes(P, R, HW, T, C):
         "render_backward": R * (28 + 4 * C) + HW * (4 * C + 8) + P * (4 * C + 24),
         "geom_backward": P * (96 + 64),
     }
-    return per_stage, sum(per_stage.values())
+    return per_stage, P * (44 + 60) + P * 8 + binning + per_stage["render_forward"] + per_stage["render_backward"] + per_stage["geom_backward"]
+
+
+class Runner:
+    """One rank's share of a workload: resident Gaussian parameters, the cameras this rank renders per step, the step functions."""
+
+    def __init__(self, a, wl, world, rank, dev, use_dist, Settings, Rast, R):
+        from seganygaussians_b200 import synthetic
+        self.a, self.wl, self.world, self.rank, self.dev, self.use_dist, self.R = a, wl, world, rank, dev, use_dist, R
+        P, H, W, K = wl["P"], wl["H"], wl["W"], wl["K"]
+        n_used = world if use_dist else 1
+        if wl["cameras"] is None:
+            self.cams = [rank % 8]                                   # weak scaling: one camera per rank
+            self.cameras_per_step = n_used
+        else:
+            self.cams = list(range(rank if use_dist else 0, wl["cameras"], n_used))     # strong scaling: camera i -> rank i mod N
+            self.cameras_per_step = wl["cameras"]
+        sc = synthetic.scene(P, H, W, K, cam=self.cams[0] if self.cams else 0)
+        self.sc = sc
+        g = sc.gauss
+        self.means3D = g.means3D.to(dev).requires_grad_(True)
+        self.means2D = torch.zeros(P, 3, device=dev, requires_grad=True)
+        self.opac = g.opacities.to(dev).requires_grad_(True)
+        self.scales = g.scales.to(dev).requires_grad_(True)
+        self.rots = g.rotations.to(dev).requires_grad_(True)
+        self.colors = g.colors.to(dev).requires_grad_(True)
+        self.leaves = (self.means3D, self.means2D, self.opac, self.scales, self.rots, self.colors)
+        self.dL = sc.dL_dout.to(dev)
+        self.Settings, self.Rast = Settings, Rast
+        self.host_cams, self.rasts = [], []
+        self.h2d_bytes = 0
+        for ci in self.cams:
+            c = synthetic.make_camera(H, W, ci)
+            dev_t = [t.to(dev) for t in (c.world_view_transform, c.full_proj_transform, c.camera_center, torch.zeros(K))]
+            self.rasts.append(Rast(raster_settings=self._settings(c, *dev_t)))
+            pinned = [t.clone().pin_memory() for t in (c.world_view_transform, c.full_proj_transform, c.camera_center, torch.zeros(K))]
+            self.host_cams.append((c, pinned))
+            self.h2d_bytes += sum(t.numel() * 4 for t in pinned)
+        self.reducer = None
+        self.own_allreduce = None
+        if use_dist and a.impl == "ours":
+            if a.allreduce == "multimem":
+                from seganygaussians_b200.data_parallel import MulticastAllReduce
+                self.own_allreduce = MulticastAllReduce(P * K, dev)
+            elif a.allreduce_mode == "overlap":
+                from seganygaussians_b200.data_parallel import FeatureGradReducer
+                self.reducer = FeatureGradReducer(side_stream=True)
+        self.last = {}
+
+    def _settings(self, c, view, proj, campos, bg):
+        wl = self.wl
+        return self.Settings(image_height=wl["H"], image_width=wl["W"], tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=bg, scale_modifier=1.0,
+                             viewmatrix=view, projmatrix=proj, sh_degree=0, campos=campos, prefiltered=False, debug=False)
+
+    def _render(self, rast):
+        return rast(means3D=self.means3D, means2D=self.means2D, opacities=self.opac, shs=None, colors_precomp=self.colors,
+                    scales=self.scales, rotations=self.rots, cov3D_precomp=None)
+
+    def _reduce(self):
+        import torch.distributed as dist
+        if self.colors.grad is None:                               # a rank without a camera still joins the collective
+            self.colors.grad = torch.zeros_like(self.colors)
+        if self.reducer is not None:
+            self.reducer.wait()                                    # at most one exchange in flight
+            self.reducer.reduce_async(self.colors.grad)            # side stream, behind everything queued so far
+            self.R.set_blend_wait_event(self.reducer.ready_event())  # next forward: geometry stages run ahead, the blend waits
+        elif self.own_allreduce is not None:
+            self.own_allreduce.all_reduce_(self.colors.grad)
+        else:
+            dist.all_reduce(self.colors.grad)
+
+    def step_resident(self):
+        for t in self.leaves:
+            t.grad = None
+        for rast in self.rasts:
+            color, radii = self._render(rast)
+            self.last["grad_fn"], self.last["radii"] = color.grad_fn, radii
+            color.backward(self.dL)
+        if self.use_dist:
+            self._reduce()
+
+    def step_e2e(self):
+        for t in self.leaves:
+            t.grad = None
+        total = None
+        for (c, pinned) in self.host_cams:
+            view, proj, campos, bg = (t.to(self.dev, non_blocking=True) for t in pinned)
+            rast = self.Rast(raster_settings=self._settings(c, view, proj, campos, bg))
+            color, radii = self._render(rast)
+            loss = (color * self.dL).sum()
+            loss.backward()
+            total = loss.detach() if total is None else total + loss.detach()
+        if self.use_dist:
+            self._reduce()
+        return float(total.item()) if total is not None else 0.0   # device -> host read of the step's result
+
+    def barrier(self):
+        if self.use_dist:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(self.dev)
+
+    def timed(self, fn, steps, sampler=None):
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = {steps // 4, steps // 2, (3 * steps) // 4} if sampler is not None and steps >= 8 else ({steps - 1} if sampler is not None else set())
+        e0.record()
+        for i in range(steps):
+            fn()
+            if i in marks:
+                sampler.sample()          # the GPU is still executing queued steps
+        if self.reducer is not None:
+            self.reducer.wait()           # the last exchange belongs to the timed region
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.use_dist:
+            import torch.distributed as dist
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def counters(self, ours: bool):
+        """Work counters of this rank's last camera, decoded from the last call's scratch."""
+        wl = self.wl
+        H, W = wl["H"], wl["W"]
+        gf = self.last["grad_fn"]
+        R_inst = int(gf.num_rendered)
+        vis = int((self.last["radii"] > 0).sum().item())
+        pairs = None
+        try:
+            img_state = gf.saved_tensors[-1]                       # both implementations save the image-state bytes last
+            if ours:
+                from seganygaussians_b200 import _lib
+                off = _lib.image_layout(W, H).n_contrib
+            else:
+                off = (4 * H * W + 127) // 128 * 128               # reference layout: accum_alpha f32[N] | n_contrib u32[N] (SURVEY.md Appendix B)
+            pairs = int(img_state[off: off + 4 * H * W].view(torch.int32).sum(dtype=torch.int64).item())
+        except Exception:
+            pairs = None
+        return R_inst, vis, pairs
+
+
+def kernel_names(a, K):
+    fwd = {"default": "mma.sync warp kernel at K=32, fp32 tile kernel otherwise", "tile": "tcgen05 tile kernel",
+           "warp_any": "mma.sync warp kernel for every K"}[a.fwd_kernel]
+    bwd = {"default": "library default (rasterizer.py)", "warp": "mma.sync warp kernel", "tile": "mma.sync tile kernel",
+           "tc": "tcgen05 / TMEM pixel-group kernel"}[a.bwd_kernel]
+    return {"forward": fwd, "backward": bwd, "binning": a.binning}
 
 
 def main():
@@ -164,18 +322,15 @@ def main():
     if use_dist:
         dist.init_process_group("nccl", device_id=dev)
 
-    from seganygaussians_b200 import synthetic
-    cam_index = rank % 8
-    sc = synthetic.scene(P, H, W, K, cam=cam_index)
-    g = sc.gauss
-
     # ---------------- implementation under test ----------------
     ref_kind = None
+    R = None
     if a.impl == "ours":
         from seganygaussians_b200 import rasterizer as R, _lib
         _lib.load()
         R.set_blend_kernels(forward=a.fwd_kernel, backward=a.bwd_kernel)
-        R.set_binning(a.binning)
+        if a.binning != "default":
+            R.set_binning(a.binning)
         Settings, Rast = R.GaussianRasterizationSettings, R.GaussianRasterizerContrastiveF
     else:
         from tests import common
@@ -184,179 +339,81 @@ def main():
             Settings, Rast = mod.GaussianRasterizationSettings, mod.GaussianRasterizer
             ref_kind = "reference-cuda-ext"
         else:
-            return reference_cpu_arm(a, wl, sc)
+            from seganygaussians_b200 import synthetic
+            return reference_cpu_arm(a, wl, synthetic.scene(P, H, W, K))
 
-    means3D = g.means3D.to(dev).requires_grad_(True)
-    means2D = torch.zeros(P, 3, device=dev, requires_grad=True)
-    opac = g.opacities.to(dev).requires_grad_(True)
-    scales = g.scales.to(dev).requires_grad_(True)
-    rots = g.rotations.to(dev).requires_grad_(True)
-    colors = g.colors.to(dev).requires_grad_(True)
-    leaves = (means3D, means2D, opac, scales, rots, colors)
-    dL = sc.dL_dout.to(dev)
-    c = sc.cam
-    bg_d = torch.zeros(K, device=dev)
-    view_d, proj_d, campos_d = c.world_view_transform.to(dev), c.full_proj_transform.to(dev), c.camera_center.to(dev)
-    # pinned host copies of the per-step inputs (e2e leg)
-    view_h, proj_h, campos_h, bg_h = (t.clone().pin_memory() for t in (c.world_view_transform, c.full_proj_transform,
-                                                                        c.camera_center, torch.zeros(K)))
-    h2d_bytes = sum(t.numel() * 4 for t in (view_h, proj_h, campos_h, bg_h))
-
-    def settings(view, proj, campos, bg):
-        return Settings(image_height=H, image_width=W, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=bg, scale_modifier=1.0,
-                        viewmatrix=view, projmatrix=proj, sh_degree=0, campos=campos, prefiltered=False, debug=False)
-
-    overlap = bool(getattr(a, "overlap_allreduce", False)) and a.impl == "ours"
-    reducer = None
-    if overlap and world > 1:
-        from seganygaussians_b200.data_parallel import FeatureGradReducer
-        reducer = FeatureGradReducer(side_stream=True)
-    own_allreduce = None
-    if a.impl == "ours" and use_dist and a.allreduce == "multimem":
-        from seganygaussians_b200.data_parallel import MulticastAllReduce
-        own_allreduce = MulticastAllReduce(P * K, dev)
-
-    def reduce_grad(t):
-        if own_allreduce is not None:
-            own_allreduce.all_reduce_(t)
-        else:
-            dist.all_reduce(t)
-
-    rs_resident = settings(view_d, proj_d, campos_d, bg_d)
-    rast_resident = Rast(raster_settings=rs_resident)
-    last = {}
-
-    def step_resident():
-        for t in leaves:
-            t.grad = None
-        color, radii = rast_resident(means3D=means3D, means2D=means2D, opacities=opac, shs=None, colors_precomp=colors,
-                                     scales=scales, rotations=rots, cov3D_precomp=None)
-        last["num_rendered"] = int(color.grad_fn.num_rendered)
-        last["radii"] = radii
-        color.backward(dL)
-        if use_dist:
-            if reducer is not None:
-                reducer.wait()                               # at most one exchange in flight
-                reducer.reduce_async(colors.grad)            # side stream, behind everything queued so far
-                R.set_blend_wait_event(reducer.ready_event())
-            else:
-                reduce_grad(colors.grad)
-
-    def step_e2e():
-        for t in leaves:
-            t.grad = None
-        view = view_h.to(dev, non_blocking=True); proj = proj_h.to(dev, non_blocking=True)
-        campos = campos_h.to(dev, non_blocking=True); bg = bg_h.to(dev, non_blocking=True)
-        rast = Rast(raster_settings=settings(view, proj, campos, bg))
-        color, radii = rast(means3D=means3D, means2D=means2D, opacities=opac, shs=None, colors_precomp=colors,
-                            scales=scales, rotations=rots, cov3D_precomp=None)
-        loss = (color * dL).sum()
-        loss.backward()
-        if use_dist:
-            reduce_grad(colors.grad)
-        return float(loss.item())   # device -> host read of the step's result
-
-    def barrier():
-        if use_dist:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def timed(fn, steps, sampler=None):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn()
-            if sampler is not None and (i == steps // 2 or i == steps - 1):
-                sampler.sample()          # the GPU is still executing this step's backward
-        if reducer is not None:
-            reducer.wait()                # the last exchange belongs to the timed region
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if use_dist:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+    run = Runner(a, wl, world, rank, dev, use_dist, Settings, Rast, R)
 
     # ---------------- warm-up, then the timed regions ----------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    for _ in range(max(a.warmup, 3)):
-        step_resident()
-    step_e2e()
-    barrier()
+    warm = max(a.warmup, 3)
+    for _ in range(warm):
+        run.step_resident()
+    run.step_e2e()
+    run.barrier()
     if a.impl == "ours":
         _lib.reset_launch_count()
+    ms_total = run.timed(run.step_resident, a.steps, sampler)
+    launches = _lib.launch_count() if a.impl == "ours" else None
+    ms_e2e = run.timed(run.step_e2e, a.steps)
+    clocks = sampler.result() if sampler else None
+    stage, stage_steps = None, min(a.steps, 20)
+    if a.impl == "ours":           # per-stage CUDA-event times: a separate pass, the instrumentation stays out of the numbers above
         _lib.profile_read(reset=True)
         _lib.profile_enable(True)
-    ms_total = timed(step_resident, a.steps, sampler)
-    stage = None
-    launches = None
-    if a.impl == "ours":
+        run.timed(run.step_resident, stage_steps)
         _lib.profile_enable(False)
         stage = _lib.profile_read(reset=True)
-        launches = _lib.launch_count()
-    ms_e2e = timed(step_e2e, a.steps)
-    clocks = sampler.result() if sampler else None
 
     n_used = world if use_dist else 1
-    gp_per_step = float(P) * H * W * n_used
+    gp_per_step = float(P) * H * W * run.cameras_per_step
     value = gp_per_step * a.steps / (ms_total * 1e-3)
     e2e_value = gp_per_step * a.steps / (ms_e2e * 1e-3)
+    R_inst, radii_vis, pairs_to_last = run.counters(a.impl == "ours")
+
+    # ---------------- BASELINE configs[3]: 8-camera batch, strong scaling ----------------
+    c4 = None
+    if not a.no_c4 and a.workload == "c2":
+        del run
+        torch.cuda.empty_cache()
+        c4 = c4_leg(a, world, rank, dev, use_dist, Settings, Rast, R)
 
     if rank != 0:
         if use_dist:
             dist.destroy_process_group()
         return 0
 
-    # ---------------- work counters of rank 0's camera ----------------
-    R_inst = last["num_rendered"]
-    radii_vis = int((last["radii"] > 0).sum().item())
     T_tiles = ((W + 15) // 16) * ((H + 15) // 16)
-    # work-proportional counters: S = pair tests a tile-per-CTA traversal would make at most
-    # (256 threads x every instance of the tile); n_contrib summed = pairs up to each pixel's last contributor.
-    S_pairs = 256 * R_inst
-    pairs_to_last = None
-    if a.impl == "ours":
-        try:   # one extra UNTIMED forward: n_contrib lives in the call's opaque image-state buffer
-            color_x, _ = rast_resident(means3D=means3D, means2D=means2D, opacities=opac, shs=None, colors_precomp=colors,
-                                       scales=scales, rotations=rots, cov3D_precomp=None)
-            img_state = color_x.grad_fn.saved_tensors[-1]
-            il = _lib.image_layout(W, H)
-            raw = img_state[il.n_contrib: il.n_contrib + 4 * H * W]
-            pairs_to_last = int(raw.view(torch.int32).sum(dtype=torch.int64).item())
-        except Exception:
-            pairs_to_last = None
+    strong = wl["cameras"] is not None
     line = {
         "metric": f"fwd+bwd Gaussians*pixels/s @K={K}", "value": value, "unit": "Gaussian*pixel/s",
-        "n_gpus": world if (use_dist or a.impl != "ours") else a.gpus, "steps": a.steps, "warmup": max(a.warmup, 3),
-        "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "n_gpus": world if (use_dist or a.impl != "ours") else a.gpus, "steps": a.steps, "warmup": warm,
+        "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "impl": a.impl,
-        "config": {"workload": wl["desc"], "P": P, "H": H, "W": W, "K": K, "cameras_per_step": n_used,
-                   "parallelism": f"camera-dp{n_used}" + ("+allreduce(dL_dcolors)" if use_dist else "") +
-                                  ("+overlapped with the next forward's geometry stages" if reducer is not None else "") +
-                                  (" [own multimem all-reduce]" if own_allreduce is not None else ""),
+        "config": {"workload": wl["desc"], "P": P, "H": H, "W": W, "K": K, "cameras_per_step": gp_per_step / (float(P) * H * W),
+                   "parallelism": f"camera-dp{n_used}" + ("+allreduce(dL_dcolors)" if use_dist else ""),
                    "l2": "inputs_exceed_l2 (features 128 MB + upstream gradient 265 MB + image 265 MB >> 126 MB L2)",
                    "P_visible": radii_vis, "R_instances": R_inst,
-                   "kernels": {"forward": {"default": "mma.sync warp kernel at K=32, fp32 tile kernel otherwise", "tile": "tcgen05 tile kernel",
-                                           "warp_any": "mma.sync warp kernel for every K"}[a.fwd_kernel],
-                               "backward": {"default": "mma.sync warp kernel", "tile": "mma.sync tile kernel", "tc": "tcgen05 / TMEM pixel-group kernel"}[a.bwd_kernel],
-                               "binning": a.binning},
-                   "S_pair_tests_upper_bound": S_pairs, "pairs_up_to_last_contributor": pairs_to_last},
+                   # work-proportional counters: S = pair tests a tile-per-CTA traversal would make at
+                   # most (256 threads x every instance of the tile); n_contrib summed = pairs up to each pixel's last contributor
+                   "S_pair_tests_upper_bound": 256 * R_inst, "pairs_up_to_last_contributor": pairs_to_last},
         "e2e": {"value": e2e_value, "unit": "Gaussian*pixel/s", "ms_per_step": ms_e2e / a.steps,
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
+                "h2d_bytes_per_step": run_h2d(wl, n_used), "d2h_bytes_per_step": 8,
                 "note": "camera from pinned host memory each step; loss scalar + num_rendered read back"},
         "clocks": clocks,
     }
     if a.impl == "ours":
+        line["kernels"] = kernel_names(a, K)
+        line["allreduce"] = None if not use_dist else (
+            "own multimem all-reduce" if a.allreduce == "multimem" else
+            ("ncclAllReduce on a side stream, gating only the next forward's blend stage" if a.allreduce_mode == "overlap" else "ncclAllReduce, serialised"))
         peak, peak_src = load_peaks()
         per_stage_bytes, step_bytes = algorithmic_bytes(P, R_inst, H * W, T_tiles, K)
-        dom = max(stage.items(), key=lambda kv: kv[1][0])
-        dom_name, (dom_ms, dom_n) = dom
+        dom_name, (dom_ms, dom_n) = max(stage.items(), key=lambda kv: kv[1][0])
         dom_avg_ms = dom_ms / max(dom_n, 1)
         achieved = per_stage_bytes[dom_name] / (dom_avg_ms * 1e-3) / 1e9
-        traffic = None
-        inst = None
+        traffic = inst = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
@@ -365,10 +422,12 @@ def main():
                 inst = prof.get("inst_executed", {}).get(dom_name)
             except Exception:
                 traffic = None
+        step_ms = ms_total / a.steps
         line["roofline"] = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": per_stage_bytes[dom_name], "avg_launch_ms": dom_avg_ms,
-                            "share_of_step": dom_ms / ms_total}
+                            "share_of_step": dom_avg_ms * len(run_cams(wl, n_used)) / step_ms,
+                            "timing": f"library stage events over a separate pass of {stage_steps} steps (instrumentation off in the value / e2e regions)"}
         if inst is not None and clocks and clocks.get("sm_mhz") and dom_avg_ms > 0:
             # the bound that actually holds for the blend kernels: warp instructions issued per second against the issue-slot
             # peak at the SM clock measured during the run (instruction count from the committed ncu capture, time live)
@@ -377,20 +436,60 @@ def main():
                                          "peak_per_s": peak_issue, "frac": inst / (dom_avg_ms * 1e-3) / peak_issue,
                                          "note": "issue-bound kernel: HBM frac is low by construction (DESIGN.md section 5)"}
         line["roofline_step"] = {"algorithmic_bytes_per_step": step_bytes,
-                                 "achieved": step_bytes / (ms_total / a.steps * 1e-3) / 1e9, "unit": "GB/s",
-                                 "frac": step_bytes / (ms_total / a.steps * 1e-3) / 1e9 / peak}
-        line["stage_ms_per_step"] = {k: v[0] / a.steps for k, v in stage.items()}
+                                 "achieved": step_bytes / (step_ms * 1e-3) / 1e9, "unit": "GB/s",
+                                 "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak}
+        line["stage_ms_per_step"] = {k: v[0] / stage_steps for k, v in stage.items()}
         line["gpu_launches"] = launches
     else:
         line["reference_kind"] = ref_kind
         line["gpu_launches"] = None
+    if c4 is not None:
+        line["c4"] = c4
     if world == 1 and not a.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(sc, K)
+        from seganygaussians_b200 import synthetic
+        line["cpu_baseline"] = cpu_baseline(synthetic.scene(P, H, W, K), K)
         line["cpu_autograd_c1"] = cpu_autograd_c1()
     print(json.dumps(line))
     if use_dist:
         dist.destroy_process_group()
     return 0
+
+
+def run_cams(wl, n_used):
+    return [0] if wl["cameras"] is None else list(range(0, wl["cameras"], n_used))
+
+
+def run_h2d(wl, n_used):
+    return len(run_cams(wl, n_used)) * (16 + 16 + 3 + wl["K"]) * 4
+
+
+def c4_leg(a, world, rank, dev, use_dist, Settings, Rast, R):
+    """BASELINE.json configs[3]: SYN(3M, 1080x1920, K=32) x 8 cameras, camera i on rank i mod N, local accumulation of the
+    feature gradient over a rank's cameras, ONE all-reduce of dL_dcolors [3M, 32] (384 MB) per batch.  Strong scaling: the
+    batch is fixed, `value` = 8 * P * H * W * steps / time (max over ranks)."""
+    wl = WORKLOADS["c4"]
+    n_used = world if use_dist else 1
+    steps = max(3, min(a.steps, 40 if a.impl == "ours" else 6) // max(1, 8 // n_used) * 1)
+    steps = max(3, min(steps, 10 if a.impl == "ours" else 3))
+    try:
+        run = Runner(a, wl, world, rank, dev, use_dist, Settings, Rast, R)
+        for _ in range(2):
+            run.step_resident()
+        run.step_e2e()
+        ms = run.timed(run.step_resident, steps)
+        ms_e2e = run.timed(run.step_e2e, steps)
+        gp = float(wl["P"]) * wl["H"] * wl["W"] * wl["cameras"]
+        R_inst, vis, pairs = run.counters(a.impl == "ours")
+        out = {"workload": wl["desc"], "scaling": "strong", "cameras_per_batch": wl["cameras"], "cameras_per_rank": len(run.cams),
+               "steps": steps, "ms_per_batch": ms / steps, "value": gp * steps / (ms * 1e-3), "unit": "Gaussian*pixel/s",
+               "e2e": {"ms_per_batch": ms_e2e / steps, "value": gp * steps / (ms_e2e * 1e-3), "h2d_bytes_per_step": run.h2d_bytes, "d2h_bytes_per_step": 8},
+               "allreduce_bytes": (wl["P"] * wl["K"] * 4) if use_dist else 0, "R_instances_last_camera": R_inst, "P_visible_last_camera": vis,
+               "parallelism": f"camera-dp{n_used}: camera i -> rank i mod {n_used}" + ("; one all-reduce(dL_dcolors) per batch" if use_dist else "")}
+        del run
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:   # the headline line must not die with the secondary leg
+        return {"workload": wl["desc"], "error": repr(e)}
 
 
 def cpu_baseline(sc, K, max_seconds=40.0):

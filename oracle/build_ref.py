@@ -92,6 +92,31 @@ def build_variant(tag: str, verbose: bool = False) -> str:
     return out_dir
 
 
+# The reference's render binding (``gaussian_renderer/__init__.py``) and the pure-Python packages its import chain
+# executes (``scene``, ``utils``, ``arguments``): installed, like the rasterizers' ``__init__.py`` above, into the
+# git-ignored output directory so that the GPU tests can drive the reference's OWN ``render*`` functions on top of the
+# reference's OWN extensions (tests/test_renderer_dropin_gpu.py).  Nothing here enters the repository history.
+RENDERER_PACKAGES = ("gaussian_renderer", "scene", "utils", "arguments")
+
+
+def install_renderer() -> str:
+    out = os.path.join(OUT_ROOT, "renderer")
+    for pkg in RENDERER_PACKAGES:
+        src = os.path.join(REF_ROOT, pkg)
+        if not os.path.isdir(src):
+            raise FileNotFoundError(src)
+        dst = os.path.join(out, pkg)
+        os.makedirs(dst, exist_ok=True)
+        for f in os.listdir(src):
+            if f.endswith(".py"):
+                shutil.copy2(os.path.join(src, f), os.path.join(dst, f))
+    return out
+
+
+def have_renderer() -> bool:
+    return os.path.exists(os.path.join(OUT_ROOT, "renderer", "gaussian_renderer", "__init__.py"))
+
+
 def have_variant(tag: str) -> bool:
     _, pkg = VARIANTS[tag]
     d = os.path.join(OUT_ROOT, pkg)
@@ -119,6 +144,8 @@ def main() -> int:
         # ``_C_v1``) when the same name is built twice with different sources in one process.
         cmd = [sys.executable, os.path.abspath(__file__), "--one", tag] + (["--verbose"] if a.verbose else [])
         subprocess.check_call(cmd)
+    if os.path.isdir(os.path.join(REF_ROOT, "gaussian_renderer")):
+        print(f"[build_ref] renderer binding installed -> {install_renderer()}")
     return 0
 
 

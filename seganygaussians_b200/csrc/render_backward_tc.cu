@@ -30,7 +30,7 @@
 namespace sagars {
 
 // two CTAs per SM: 2 x (dynamic + 1 KB reserved per CTA) must fit the SM's 228 KB
-static_assert(sizeof(BtSmem<16>) + 1024 <= 115712, "tcgen05 backward: shared memory of one CTA exceeds half an SM");
+static_assert(sizeof(BtSmem) + 1024 <= 115712, "tcgen05 backward: shared memory of one CTA exceeds half an SM");
 
 int launch_render_backward_tc(const sagars_backward_args& a, const Dims& d, GeomView g, ImageView im,
                               const uint32_t* point_list, float* ggrad, cudaStream_t s, bool debug)
@@ -39,8 +39,8 @@ int launch_render_backward_tc(const sagars_backward_args& a, const Dims& d, Geom
         set_error("the tcgen05 backward kernel handles C = %d precomputed colours only", BT_C);
         return SAGARS_EINVAL;
     }
-    auto kern = render_backward_tc_kernel<16>;
-    const size_t smem = sizeof(BtSmem<16>) + 1024;
+    auto kern = render_backward_tc_kernel;
+    const size_t smem = sizeof(BtSmem) + 1024;
     {   // opt in to the dynamic shared-memory size once per device
         static uint64_t done_mask = 0;
         int dev = 0;
@@ -52,7 +52,7 @@ int launch_render_backward_tc(const sagars_backward_args& a, const Dims& d, Geom
         }
     }
     dim3 grid(d.tiles_x, 2 * d.tiles_y);
-    kern<<<grid, BT_PIX, smem, s>>>(im.ranges, point_list, d.W, d.H, a.background, g.geo, a.colors_precomp, im.final_T, im.n_contrib,
+    kern<<<grid, BT_THREADS, smem, s>>>(im.ranges, point_list, d.W, d.H, a.background, g.geo, a.colors_precomp, im.final_T, im.n_contrib,
                                     a.dL_dout_color, ggrad, a.dL_dcolors);
     SAGARS_LAUNCH_CHECK(s, debug);
     return SAGARS_OK;

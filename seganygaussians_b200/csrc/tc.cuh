@@ -43,6 +43,13 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t a_desc, uint6
                  ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// the same with the A operand (M = 128 rows = TMEM lanes, 8 tf32 = 8 columns per instruction) in tensor memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p; }"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 // make all previously issued MMAs of this thread arrive on `bar` when they have completed
 __device__ __forceinline__ void commit(uint64_t* bar)
 {
@@ -55,6 +62,12 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 }
 __device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+// one arrival of the calling thread (release semantics at CTA scope: its earlier shared-memory writes are visible to a waiter)
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
 {
     uint32_t ok;
@@ -62,6 +75,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// non-blocking test of the same condition (a role that polls several barriers in turn)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// a published counter in shared memory: release store / acquire load at CTA scope
+__device__ __forceinline__ void st_release_cta(int* p, int v) { asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire_cta(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void backoff(unsigned ns) { __nanosleep(ns); }
+
 // wait for the phase with the given parity to complete (try_wait blocks in hardware for a bounded time per call)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
@@ -102,6 +133,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v)
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
+// this thread's TMEM lane (row), 8 consecutive columns starting at taddr's column
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v)
+{
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// registers -> this thread's TMEM lane, 32 consecutive columns (complete when the function returns)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+                 "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+                 ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+                   "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]),
+                   "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]),
+                   "f"(v[30]), "f"(v[31]) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // this thread's TMEM lane (row), 16 consecutive columns starting at taddr's column
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
 {
@@ -117,6 +171,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
 
 // 128-thread named barrier (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void bar_sync_128(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+// "f" constraints on tcgen05.st need b32 registers: floats are fine (bit pattern is stored)
 
 #endif  // SAGARS_CUDA_EMU (tests/cuda_emu/tc_emu.h restates the functions above for the CPU execution shim)
 

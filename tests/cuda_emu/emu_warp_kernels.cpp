@@ -101,7 +101,7 @@ extern "C" int emu_backward_tc(int W, int H, const uint2* ranges, const uint32_t
 {
     cuda_emu::thread_exit_hook = emu_async::flush_thread;
     const unsigned tx = (W + TILE_X - 1) / TILE_X, ty = (H + TILE_Y - 1) / TILE_Y;
-    cuda_emu::launch2d(tx, 2 * ty, BT_PIX, sizeof(BtSmem<16>) + 1024, render_backward_tc_kernel<16>, ranges, point_list, W, H, bg, geo, features,
+    cuda_emu::launch2d(tx, 2 * ty, BT_THREADS, sizeof(BtSmem) + 1024, render_backward_tc_kernel, ranges, point_list, W, H, bg, geo, features,
                        final_T, n_contrib, dL_dpix, ggrad, dL_dcolors);
     return 0;
 }

@@ -21,7 +21,7 @@ namespace sagars {
 namespace tc {
 
 namespace emu {
-struct Mma { uint32_t tmem_d; uint64_t a_desc, b_desc; uint32_t idesc, accumulate; };
+struct Mma { uint32_t tmem_d; uint64_t a_desc, b_desc; uint32_t idesc, accumulate; int a_tmem = 0; };
 struct Bar { int init = 0, pending = 0; unsigned phase = 0; std::vector<Mma> in_flight; };
 inline std::mutex mu;
 inline std::map<const void*, Bar> bars;
@@ -58,7 +58,12 @@ inline void execute(const Mma& m)
     for (int r = 0; r < M; r++)
         for (int n = 0; n < N; n++) {
             double acc = m.accumulate ? (double)tmem[lane0 + r][col0 + n] : 0.0;
-            for (int k = 0; k < 8; k++) acc += (a_mn ? elem_mn(a0, a_lbo, a_sbo, r, k) : elem(a0, a_lbo, a_sbo, r, k)) * elem(b0, b_lbo, b_sbo, n, k);
+            for (int k = 0; k < 8; k++) {
+                // A in tensor memory: row r = lane (lane field of the address) + r, 8 consecutive columns
+                const double av = m.a_tmem ? (double)tf32(tmem[(int)((uint32_t)m.a_desc >> 16) + r][(int)(m.a_desc & 0xFFFF) + k])
+                                           : (a_mn ? elem_mn(a0, a_lbo, a_sbo, r, k) : elem(a0, a_lbo, a_sbo, r, k));
+                acc += av * elem(b0, b_lbo, b_sbo, n, k);
+            }
             tmem[lane0 + r][col0 + n] = (float)acc;
         }
 }
@@ -85,13 +90,20 @@ inline void mma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t
 {
     emu::issued.push_back({tmem_d, a_desc, b_desc, idesc, accumulate});
 }
+inline void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    emu::Mma m{tmem_d, (uint64_t)tmem_a, b_desc, idesc, accumulate};
+    m.a_tmem = 1;
+    emu::issued.push_back(m);
+}
 inline void commit(uint64_t* bar)
 {
     std::lock_guard<std::mutex> lk(emu::mu);
     emu::Bar& b = emu::bars.at(bar);
     b.in_flight.insert(b.in_flight.end(), emu::issued.begin(), emu::issued.end());
     emu::issued.clear();
-    b.in_flight.push_back({0xFFFFFFFFu, 0, 0, 0, 0});          // marker: one arrival once everything before it has executed
+    emu::Mma marker{0xFFFFFFFFu, 0, 0, 0, 0};
+    b.in_flight.push_back(marker);                             // marker: one arrival once everything before it has executed
 }
 inline void mbar_init(uint64_t* bar, uint32_t count)
 {
@@ -101,6 +113,12 @@ inline void mbar_init(uint64_t* bar, uint32_t count)
     b.init = b.pending = (int)count;
 }
 inline void mbar_init_fence() {}
+inline void mbar_arrive(uint64_t* bar)                         // a thread's own arrival: immediate
+{
+    std::lock_guard<std::mutex> lk(emu::mu);
+    emu::Bar& b = emu::bars.at(bar);
+    if (--b.pending == 0) { b.phase ^= 1u; b.pending = b.init; }
+}
 inline bool mbar_try_wait(uint64_t* bar, uint32_t parity)
 {
     std::lock_guard<std::mutex> lk(emu::mu);
@@ -117,15 +135,32 @@ inline bool mbar_try_wait(uint64_t* bar, uint32_t parity)
     }
     return b.phase != (parity & 1u);
 }
+inline bool mbar_test_wait(uint64_t* bar, uint32_t parity) { return mbar_try_wait(bar, parity); }
+inline void st_release_cta(int* p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline int ld_acquire_cta(const int* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void backoff(unsigned) { std::this_thread::sleep_for(std::chrono::microseconds(20)); }
 inline void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(20);
     while (!mbar_try_wait(bar, parity)) {
         if (std::chrono::steady_clock::now() > deadline) {
-            std::fprintf(stderr, "[cuda_emu] tcgen05 mbarrier wait timed out (parity %u)\n", parity);
+            {
+                std::lock_guard<std::mutex> lk(emu::mu);
+                const emu::Bar& b = emu::bars.at(bar);
+                std::fprintf(stderr, "[cuda_emu] tcgen05 mbarrier wait timed out: thread %u block (%u,%u) parity %u, barrier at smem+%td: count %d pending %d "
+                             "phase %u, %zu operations in flight\n", threadIdx.x, blockIdx.x, blockIdx.y, parity,
+                             (const unsigned char*)bar - ::cuda_emu::dynamic_smem, b.init, b.pending, b.phase, b.in_flight.size());
+                for (const auto& kv : emu::bars) {
+                    const ptrdiff_t off = (const unsigned char*)kv.first - ::cuda_emu::dynamic_smem;
+                    if (off >= 0 && off < (1 << 20))
+                        std::fprintf(stderr, "[cuda_emu]   barrier smem+%td: count %d pending %d phase %u in flight %zu\n", off, kv.second.init,
+                                     kv.second.pending, kv.second.phase, kv.second.in_flight.size());
+                }
+            }
             std::abort();
         }
-        std::this_thread::yield();
+        // back off: hundreds of polling threads otherwise starve the one thread everybody is waiting for (emu::mu is not fair)
+        std::this_thread::sleep_for(std::chrono::microseconds(50));
     }
 }
 inline void fence_smem_to_async_proxy() {}
@@ -137,6 +172,16 @@ inline void tmem_ld32(uint32_t taddr, float* v)
 {
     const int lane = (int)(taddr >> 16) + (int)(threadIdx.x & 31), col = (int)(taddr & 0xFFFF);
     for (int i = 0; i < 32; i++) v[i] = emu::tmem[lane][col + i];
+}
+inline void tmem_ld8(uint32_t taddr, float* v)
+{
+    const int lane = (int)(taddr >> 16) + (int)(threadIdx.x & 31), col = (int)(taddr & 0xFFFF);
+    for (int i = 0; i < 8; i++) v[i] = emu::tmem[lane][col + i];
+}
+inline void tmem_st32(uint32_t taddr, const float* v)
+{
+    const int lane = (int)(taddr >> 16) + (int)(threadIdx.x & 31), col = (int)(taddr & 0xFFFF);
+    for (int i = 0; i < 32; i++) emu::tmem[lane][col + i] = v[i];
 }
 inline void tmem_ld16(uint32_t taddr, float* v)
 {

@@ -123,3 +123,45 @@ def test_dropin_packages_resolve_to_this_library():
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT,
                          env={**os.environ, "PYTHONPATH": ROOT})
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr
+
+
+def test_dropin_gaussian_renderer_ships_network_gui():
+    """The reference's train_scene.py:17 does ``from gaussian_renderer import render, network_gui``; once the drop-in package
+    shadows the reference's, that import must keep working and the module must carry the surface the training loop uses
+    (train_scene.py:56-69,228; reference gaussian_renderer/network_gui.py:21-57), speaking the viewer's wire protocol."""
+    code = r'''
+import json, socket, threading
+import seganygaussians_b200 as S; S.activate()
+from gaussian_renderer import render, network_gui
+assert 'seganygaussians_b200' in network_gui.__file__
+for n in ('host', 'port', 'conn', 'addr', 'listener', 'init', 'try_connect', 'read', 'send', 'receive'):
+    assert hasattr(network_gui, n), n
+assert network_gui.conn is None
+probe = socket.socket(); probe.bind(('127.0.0.1', 0)); port = probe.getsockname()[1]; probe.close()
+network_gui.init('127.0.0.1', port)
+network_gui.try_connect()                       # nobody there: returns at once, conn stays None
+assert network_gui.conn is None
+got = {}
+def viewer():
+    c = socket.create_connection(('127.0.0.1', port))
+    msg = json.dumps({'resolution_x': 0, 'resolution_y': 0}).encode()
+    c.sendall(len(msg).to_bytes(4, 'little') + msg)
+    n = int.from_bytes(c.recv(4), 'little')     # no image payload, then the length-prefixed tag
+    got['tag'] = c.recv(n).decode('ascii')
+    c.close()
+t = threading.Thread(target=viewer); t.start()
+import time
+for _ in range(200):
+    network_gui.try_connect()
+    if network_gui.conn is not None: break
+    time.sleep(0.01)
+assert network_gui.conn is not None
+assert network_gui.receive() == (None, None, None, None, None, None)   # zero resolution: "no camera"
+network_gui.send(None, 'some/dataset/path')
+t.join(5)
+assert got.get('tag') == 'some/dataset/path'
+print('ok')
+'''
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=120,
+                         env={**os.environ, "PYTHONPATH": ROOT})
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
