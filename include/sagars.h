@@ -82,6 +82,9 @@ enum {
                                         sorts its own segment (tile_sort.cu) instead of duplicate + 6 radix passes + range
                                         detection.  Bit-identical point_list / keys / ranges; opt-in until measured            */
 
+#define SAGARS_FLAG_DEPTH_FIRST 4096u /* binning: sort the P Gaussians by depth (4 passes over P), emit their instances in that order, then ONE
+                                        stable sort of the instances on the tile bits (2 passes for <= 65,536 tiles) instead of 6 passes
+                                        over the R duplicated (tile | depth) keys.  Bit-identical point_list / keys / ranges          */
 #define SAGARS_FLAG_BWD_TC 2048u     /* backward at C = 32 precomputed colours: tcgen05 / TMEM kernel, one CTA per 16x8 pixel group
                                         (render_backward_tc.cu) instead of the mma.sync warp-per-block kernel                  */
 

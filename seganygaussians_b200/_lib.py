@@ -27,6 +27,7 @@ FLAG_NO_TENSOR_CORES = 32
 FLAG_FWD_TILE = 64
 FLAG_BWD_TILE = 128
 FLAG_BWD_TC = 2048
+FLAG_DEPTH_FIRST = 4096
 FLAG_FWD_WARP_ANY = 256
 FLAG_STAGE_TMA = 512
 FLAG_TILE_SORT = 1024

@@ -316,6 +316,13 @@ int sagars_forward(const sagars_forward_args* a,
     const int num_tiles = d.tiles_x * d.tiles_y;
     const int end_bit = 32 + (int)higher_msb((uint32_t)num_tiles);
     const bool use_cub = (a->flags & SAGARS_FLAG_CUB_SORT) != 0;
+    // depth-first binning: the Gaussians' depth order needs nothing but P, so it is queued BEFORE the host waits for the count
+    const bool depth_first = (a->flags & SAGARS_FLAG_DEPTH_FIRST) != 0 && !use_cub && !(a->flags & SAGARS_FLAG_TILE_SORT);
+    if (depth_first) {
+        ProfScope ps(ST_SORT, s);
+        rc = launch_depth_order(d, g, s, debug);
+        if (rc) return rc;
+    }
     bool speculative = a->binning_capacity_hint > 0 && !use_cub && !debug;
     int R = 0, cap = 0;
     if (speculative) {
@@ -334,7 +341,23 @@ int sagars_forward(const sagars_forward_args* a,
         // the tile sort's queue of long segments lives in the radix sort's scratch (>= 1 MB); absurdly many tiles: radix path
         const bool tile_sort = (a->flags & SAGARS_FLAG_TILE_SORT) != 0 && !use_cub &&
                                tile_sort_queue_bytes(num_tiles) <= sort_temp_bytes((size_t)cap);
-        if (cap > 0 && tile_sort) {
+        if (depth_first) {
+            if (cap > 0) {
+                // tile-id keys live in the (unused) 64-bit alternate key array; values ping-pong between point_list and vals_alt
+                uint32_t* tk_a = reinterpret_cast<uint32_t*>(bv.keys_alt);
+                uint32_t* tk_b = tk_a + cap;
+                const int tile_bits = end_bit - 32;
+                const bool start_b = (sort_num_passes(tile_bits) & 1) != 0;
+                { ProfScope ps(ST_DUPLICATE, s); rc = launch_emit_sorted(d, g, a->radii, start_b ? tk_b : tk_a, start_b ? bv.vals_alt : bv.point_list, n_dev, cap, s, debug); }
+                if (rc) return rc;
+                { ProfScope ps(ST_SORT, s); rc = launch_sort_pairs32(n_dev, cap, tile_bits, tk_a, bv.point_list, tk_b, bv.vals_alt, bv.sort_temp, s, debug); }
+                if (rc) return rc;
+                { ProfScope ps(ST_RANGES, s); rc = launch_finalize_bins(n_dev, cap, num_tiles, tk_a, bv.point_list, g.depths, bv.point_list_keys, im.ranges, s, debug); }
+                if (rc) return rc;
+            } else {
+                SAGARS_CUDA(cudaMemsetAsync(im.ranges, 0, (size_t)num_tiles * sizeof(uint2), s));
+            }
+        } else if (cap > 0 && tile_sort) {
             // no global sort: per-tile counts -> scan -> scatter (the tile ranges fall out), then one CTA per tile sorts its
             // own segment (tile_sort.cu).  keys_alt holds the unsorted (depth bits, id) pairs.
             { ProfScope ps(ST_DUPLICATE, s); rc = launch_tile_bin(d, g, a->radii, bv.keys_alt, im.ranges, (uint32_t*)bv.sort_temp, n_dev, cap, s, debug); }

@@ -74,14 +74,79 @@ int launch_sort_pairs(const uint32_t* n_dev, int cap, int end_bit, uint64_t* key
     uint32_t* vout = (npass & 1) ? vals_a : vals_b;
     for (int p = 0; p < npass; p++) {
         const int shift = p * SORT_RADIX_BITS;
-        radix_hist_kernel<<<nblk, 256, 0, s>>>(kin, n_dev, cap, shift, counts, nblk);
+        radix_hist_kernel<uint64_t><<<nblk, 256, 0, s>>>(kin, n_dev, cap, shift, counts, nblk);
         SAGARS_LAUNCH_CHECK(s, debug);
         radix_rowscan_kernel<<<SORT_RADIX * 32 / 256, 256, 0, s>>>(counts, nblk, totals);
         SAGARS_LAUNCH_CHECK(s, debug);
-        radix_scatter_kernel<<<nblk, 256, 0, s>>>(kin, vin, kout, vout, n_dev, cap, shift, counts, totals, nblk);
+        radix_scatter_kernel<uint64_t><<<nblk, 256, 0, s>>>(kin, vin, kout, vout, n_dev, cap, shift, counts, totals, nblk);
         SAGARS_LAUNCH_CHECK(s, debug);
         uint64_t* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;
+    }
+    return SAGARS_OK;
+}
+
+// 32-bit keys: the pairs must be in (keys_a, vals_a) when the pass count is even and in (keys_b, vals_b) when it is odd; the result
+// lands in (keys_a, vals_a).  n = *n_dev (device) or, with n_dev == nullptr, cap.
+int launch_sort_pairs32(const uint32_t* n_dev, int cap, int end_bit, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
+                        void* temp, cudaStream_t s, bool debug)
+{
+    if (cap <= 0) return SAGARS_OK;
+    const int nblk = (cap + SORT_CHUNK - 1) / SORT_CHUNK;
+    uint32_t* counts = (uint32_t*)temp;
+    uint32_t* totals = (uint32_t*)((char*)temp + align_up((size_t)SORT_RADIX * (nblk + 1) * 4));
+    const int npass = sort_num_passes(end_bit);
+    uint32_t* kin = (npass & 1) ? keys_b : keys_a;
+    uint32_t* vin = (npass & 1) ? vals_b : vals_a;
+    uint32_t* kout = (npass & 1) ? keys_a : keys_b;
+    uint32_t* vout = (npass & 1) ? vals_a : vals_b;
+    for (int p = 0; p < npass; p++) {
+        const int shift = p * SORT_RADIX_BITS;
+        radix_hist_kernel<uint32_t><<<nblk, 256, 0, s>>>(kin, n_dev, cap, shift, counts, nblk);
+        SAGARS_LAUNCH_CHECK(s, debug);
+        radix_rowscan_kernel<<<SORT_RADIX * 32 / 256, 256, 0, s>>>(counts, nblk, totals);
+        SAGARS_LAUNCH_CHECK(s, debug);
+        radix_scatter_kernel<uint32_t><<<nblk, 256, 0, s>>>(kin, vin, kout, vout, n_dev, cap, shift, counts, totals, nblk);
+        SAGARS_LAUNCH_CHECK(s, debug);
+        uint32_t* tk = kin; kin = kout; kout = tk;
+        uint32_t* tv = vin; vin = vout; vout = tv;
+    }
+    return SAGARS_OK;
+}
+
+// Gaussians in depth order (g.ovals[0]) and the exclusive scan of their tile counts in that order (g.order_sums); also
+// point_offsets.  Needs the preprocess outputs and the scanned block sums only, not the instance count.
+int launch_depth_order(const Dims& d, GeomView g, cudaStream_t s, bool debug)
+{
+    const int nblk = (d.P + 255) / 256;
+    order_keys_kernel<<<nblk, 256, 0, s>>>(d.P, g.depths, g.tiles_touched, g.block_sums, g.point_offsets, g.okeys[0], g.ovals[0]);
+    SAGARS_LAUNCH_CHECK(s, debug);
+    int rc = launch_sort_pairs32(nullptr, d.P, 32, g.okeys[0], g.ovals[0], g.okeys[1], g.ovals[1], g.osort_temp, s, debug);
+    if (rc) return rc;
+    sorted_block_sums_kernel<<<nblk, 256, 0, s>>>(d.P, g.ovals[0], g.tiles_touched, g.order_sums);
+    SAGARS_LAUNCH_CHECK(s, debug);
+    scan_block_sums_kernel<<<1, 1024, 0, s>>>(g.order_sums, nblk, g.status);      // status[1] = the same total once more
+    SAGARS_LAUNCH_CHECK(s, debug);
+    return SAGARS_OK;
+}
+
+int launch_emit_sorted(const Dims& d, GeomView g, const int32_t* radii, uint32_t* tkeys, uint32_t* vals, const uint32_t* n_dev, int cap,
+                       cudaStream_t s, bool debug)
+{
+    const int nblk = (d.P + 255) / 256;
+    emit_sorted_kernel<<<nblk, 256, 0, s>>>(d.P, g.ovals[0], g.geo, g.tiles_touched, g.order_sums, radii, tkeys, vals, d.tiles_x, d.tiles_y,
+                                            n_dev, cap);
+    SAGARS_LAUNCH_CHECK(s, debug);
+    return SAGARS_OK;
+}
+
+int launch_finalize_bins(const uint32_t* n_dev, int cap, int num_tiles, const uint32_t* tkeys, const uint32_t* point_list, const float* depths,
+                         uint64_t* keys, uint2* ranges, cudaStream_t s, bool debug)
+{
+    SAGARS_CUDA(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), s));
+    if (cap > 0) {
+        finalize_bins_kernel<<<(cap + 255) / 256, 256, 0, s>>>(n_dev, cap, tkeys, point_list, depths, keys, ranges);
+        SAGARS_LAUNCH_CHECK(s, debug);
     }
     return SAGARS_OK;
 }

@@ -120,8 +120,9 @@ duplicate_kernel(int P, const float* __restrict__ geo, const float* __restrict__
 // ---------------------------------------------------------------------------------------------
 // stable LSD radix sort of (u64 key, u32 value), 8-bit digits
 // ---------------------------------------------------------------------------------------------
+template <class KeyT>
 __global__ void __launch_bounds__(256)
-radix_hist_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ n_dev, int cap, int shift,
+radix_hist_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ n_dev, int cap, int shift,
                   uint32_t* __restrict__ counts, int nblk)
 {
     __shared__ uint32_t hist[SORT_RADIX];
@@ -163,9 +164,10 @@ radix_rowscan_kernel(uint32_t* __restrict__ counts, int nblk, uint32_t* __restri
     if (lane == 0) totals[dgt] = carry;
 }
 
+template <class KeyT>
 __global__ void __launch_bounds__(256)
-radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                     uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+radix_scatter_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                     KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                      const uint32_t* __restrict__ n_dev, int cap, int shift,
                      const uint32_t* __restrict__ counts, const uint32_t* __restrict__ totals, int nblk)
 {
@@ -201,7 +203,7 @@ radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __res
         const int buf = r & 1;
         const int i = start + r * 256 + tid;
         const bool valid = i < n;
-        uint64_t key = 0;
+        KeyT key = 0;
         uint32_t val = 0;
         uint32_t dgt = 0xffffffffu - (uint32_t)lane;   // unique per lane: never matches a real digit
         if (valid) {
@@ -233,6 +235,126 @@ radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __res
         for (int w = 0; w < 8; w++) warp_cnt[buf ^ 1][w][tid] = 0;
         __syncthreads();
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// DEPTH-FIRST binning (SAGARS_FLAG_DEPTH_FIRST, the default): the same point_list / keys / ranges with a quarter of the sort
+// traffic.  The reference sorts the R = sum(tiles_touched) duplicated instances on 32 depth bits + the tile bits (6 passes over
+// R 12-byte pairs).  Equivalent, because an LSD radix sort is stable and so is every step below:
+//   1. sort the P GAUSSIANS by depth bits (4 passes over P 8-byte pairs; culled Gaussians get the key 0xFFFFFFFF and sort last);
+//   2. emit each Gaussian's instances in that order -> the instance array is already ordered by (depth, Gaussian index);
+//   3. a stable sort of the instances on the TILE bits only (2 passes for up to 65,536 tiles) leaves every tile's segment in
+//      (depth, index) order = exactly the order of the reference's stable sort on (tile | depth) keys emitted in index order;
+//   4. the 64-bit keys of the reference are rebuilt from (tile, depth of the Gaussian) while the tile ranges are detected.
+// ---------------------------------------------------------------------------------------------
+
+// Step 1a (P threads, the preprocess kernel's 256-Gaussian blocks): point_offsets (inclusive scan of tiles_touched in index
+// order: part of the geometry state) and the Gaussian's sort key.
+__global__ void __launch_bounds__(256)
+order_keys_kernel(int P, const float* __restrict__ depths, const uint32_t* __restrict__ tiles_touched,
+                  const uint32_t* __restrict__ block_excl, uint32_t* __restrict__ point_offsets,
+                  uint32_t* __restrict__ okeys, uint32_t* __restrict__ ovals)
+{
+    __shared__ uint32_t warp_tot[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int idx = blockIdx.x * 256 + tid;
+    const uint32_t n = (idx < P) ? tiles_touched[idx] : 0u;
+    uint32_t inc = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) wbase += (w < warp) ? warp_tot[w] : 0u;
+    if (idx >= P) return;
+    point_offsets[idx] = block_excl[blockIdx.x] + wbase + inc;
+    okeys[idx] = n ? __float_as_uint(depths[idx]) : 0xFFFFFFFFu;     // view depth > 0.2: raw bits are monotone
+    ovals[idx] = (uint32_t)idx;
+}
+
+// Step 2a: per-256-block sums of tiles_touched taken in depth order (input of scan_block_sums_kernel)
+__global__ void __launch_bounds__(256)
+sorted_block_sums_kernel(int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles_touched,
+                         uint32_t* __restrict__ block_sums)
+{
+    __shared__ uint32_t warp_tot[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = blockIdx.x * 256 + tid;
+    uint32_t n = (i < P) ? tiles_touched[order[i]] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if (lane == 0) warp_tot[warp] = n;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) s += warp_tot[w];
+        block_sums[blockIdx.x] = s;
+    }
+}
+
+// Step 2b: instance emission in depth order: (tile id, Gaussian index) pairs, tiles y-outer / x-inner as the reference
+__global__ void __launch_bounds__(256)
+emit_sorted_kernel(int P, const uint32_t* __restrict__ order, const float* __restrict__ geo, const uint32_t* __restrict__ tiles_touched,
+                   const uint32_t* __restrict__ block_excl, const int32_t* __restrict__ radii,
+                   uint32_t* __restrict__ tkeys, uint32_t* __restrict__ vals, int tiles_x, int tiles_y,
+                   const uint32_t* __restrict__ n_dev, int cap)
+{
+    __shared__ uint32_t warp_tot[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = blockIdx.x * 256 + tid;
+    const uint32_t idx = (i < P) ? order[i] : 0u;
+    const uint32_t n = (i < P) ? tiles_touched[idx] : 0u;
+    uint32_t inc = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) wbase += (w < warp) ? warp_tot[w] : 0u;
+    if (i >= P || n == 0) return;
+    if (n_dev != nullptr && *n_dev > (uint32_t)cap) return;   // layout too small: nothing may be written
+    uint32_t off = block_excl[blockIdx.x] + wbase + inc - n;
+    const float4 r0 = *reinterpret_cast<const float4*>(geo + 8 * (size_t)idx);
+    uint2 rmin, rmax;
+    tile_rect(make_float2(r0.x, r0.y), radii[idx], rmin, rmax, tiles_x, tiles_y);
+    for (uint32_t y = rmin.y; y < rmax.y; y++) {
+        for (uint32_t x = rmin.x; x < rmax.x; x++) {
+            tkeys[off] = y * (uint32_t)tiles_x + x;
+            vals[off] = idx;
+            off++;
+        }
+    }
+}
+
+// Step 4: the reference's 64-bit keys (tile << 32 | depth bits) and the tile ranges from the tile-sorted instances
+__global__ void __launch_bounds__(256)
+finalize_bins_kernel(const uint32_t* __restrict__ n_dev, int cap, const uint32_t* __restrict__ tkeys, const uint32_t* __restrict__ point_list,
+                     const float* __restrict__ depths, uint64_t* __restrict__ keys, uint2* __restrict__ ranges)
+{
+    const int R = live_count(n_dev, cap);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const uint32_t cur = tkeys[i];
+    keys[i] = ((uint64_t)cur << 32) | (uint64_t)__float_as_uint(depths[point_list[i]]);
+    if (i == 0) {
+        ranges[cur].x = 0;
+    } else {
+        const uint32_t prev = tkeys[i - 1];
+        if (cur != prev) {
+            ranges[prev].y = (uint32_t)i;
+            ranges[cur].x = (uint32_t)i;
+        }
+    }
+    if (i == R - 1) ranges[cur].y = (uint32_t)R;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -41,12 +41,29 @@ struct GeomView {
     uint32_t* point_offsets;  // [P]  inclusive prefix sum of tiles_touched
     uint32_t* block_sums;     // [ceil(P/256)+1]  per-preprocess-block sums, then their exclusive scan
     uint32_t* status;         // [8]  0: prefilter violation flag, 1: num_rendered
+    // depth-first binning (binning_kernels.cuh): the Gaussians ordered by depth
+    uint32_t* okeys[2];       // [P] depth bits (0xFFFFFFFF when culled), ping-pong
+    uint32_t* ovals[2];       // [P] Gaussian indices, ping-pong; after the sort ovals[0] is the depth order
+    uint32_t* order_sums;     // [ceil(P/256)+1] block sums of tiles_touched taken in depth order, then their exclusive scan
+    void* osort_temp;         // radix-sort scratch for P pairs
 };
 
 struct GeomOffsets {
     sagars_geom_layout pub;
     size_t block_sums;
+    size_t okeys[2], ovals[2], order_sums, osort_temp;
 };
+#ifndef SAGARS_SORT_CONSTANTS
+#define SAGARS_SORT_CONSTANTS
+constexpr int SORT_CHUNK = 4096;          // keys per sort block
+constexpr int SORT_RADIX_BITS = 8;
+constexpr int SORT_RADIX = 1 << SORT_RADIX_BITS;
+#endif
+// own radix sort: counts[RADIX][nblk] + totals[RADIX]
+inline size_t own_sort_temp_bytes(size_t n) {
+    size_t nblk = (n + SORT_CHUNK - 1) / SORT_CHUNK;
+    return align_up((size_t)SORT_RADIX * (nblk + 1) * 4) + align_up(SORT_RADIX * 4);
+}
 inline GeomOffsets geom_offsets(size_t P) {
     GeomOffsets G;
     sagars_geom_layout& L = G.pub;
@@ -61,6 +78,10 @@ inline GeomOffsets geom_offsets(size_t P) {
     size_t nblk = (P + 255) / 256 + 1;
     G.block_sums = o;    o = align_up(o + nblk * 4);
     L.status = o;        o = align_up(o + 64);
+    for (int k = 0; k < 2; k++) { G.okeys[k] = o; o = align_up(o + P * 4); }
+    for (int k = 0; k < 2; k++) { G.ovals[k] = o; o = align_up(o + P * 4); }
+    G.order_sums = o;    o = align_up(o + nblk * 4);
+    G.osort_temp = o;    o = align_up(o + own_sort_temp_bytes(P));
     L.total = o + 256;
     return G;
 }
@@ -79,6 +100,9 @@ inline GeomView geom_view(void* base, size_t P) {
     g.point_offsets = (uint32_t*)(b + L.point_offsets);
     g.block_sums = (uint32_t*)(b + G.block_sums);
     g.status = (uint32_t*)(b + L.status);
+    for (int k = 0; k < 2; k++) { g.okeys[k] = (uint32_t*)(b + G.okeys[k]); g.ovals[k] = (uint32_t*)(b + G.ovals[k]); }
+    g.order_sums = (uint32_t*)(b + G.order_sums);
+    g.osort_temp = (void*)(b + G.osort_temp);
     return g;
 }
 
@@ -124,9 +148,8 @@ struct BinningView {
     void* sort_temp;             // sort_temp_bytes(R)
 };
 inline size_t sort_temp_bytes(size_t n) {
-    size_t nblk = (n + SORT_CHUNK - 1) / SORT_CHUNK;
     // own sort: counts[RADIX][nblk] + totals[RADIX];  CUB (DoubleBuffer) needs O(n / tile) look-back state
-    size_t own = align_up((size_t)SORT_RADIX * (nblk + 1) * 4) + align_up(SORT_RADIX * 4);
+    size_t own = own_sort_temp_bytes(n);
     size_t cub = align_up(n / 2 + (1u << 20));
     return own > cub ? own : cub;
 }
@@ -205,6 +228,14 @@ int launch_sort_pairs(const uint32_t* n_dev, int cap, int end_bit, uint64_t* key
                       cudaStream_t s, bool debug);
 int sort_num_passes(int end_bit);
 int launch_tile_ranges(const uint32_t* n_dev, int cap, int num_tiles, const uint64_t* keys, uint2* ranges, cudaStream_t s, bool debug);
+// depth-first binning (SAGARS default): Gaussians ordered by depth -> instances emitted in that order -> stable sort on the tile bits
+int launch_depth_order(const Dims& d, GeomView g, cudaStream_t s, bool debug);            // needs only P: may run before R is known
+int launch_emit_sorted(const Dims& d, GeomView g, const int32_t* radii, uint32_t* tkeys, uint32_t* vals, const uint32_t* n_dev, int cap,
+                       cudaStream_t s, bool debug);
+int launch_sort_pairs32(const uint32_t* n_dev, int cap, int end_bit, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
+                        void* temp, cudaStream_t s, bool debug);                           // input in A (even pass count) or B (odd); result in A
+int launch_finalize_bins(const uint32_t* n_dev, int cap, int num_tiles, const uint32_t* tkeys, const uint32_t* point_list, const float* depths,
+                         uint64_t* keys, uint2* ranges, cudaStream_t s, bool debug);
 // tile_sort.cu (SAGARS_FLAG_TILE_SORT): count -> scan -> scatter (launch_tile_bin), then one CTA per tile sorts its segment
 int launch_tile_bin(const Dims& d, GeomView g, const int32_t* radii, uint64_t* pairs, uint2* ranges, uint32_t* queue,
                     const uint32_t* n_dev, int cap, cudaStream_t s, bool debug);

@@ -140,6 +140,8 @@ def _flags(settings: GaussianRasterizationSettings, extra: int = 0) -> int:
         f |= _lib.FLAG_STAGE_TMA
     if _BINNING == "tile_sort":
         f |= _lib.FLAG_TILE_SORT
+    elif _BINNING == "depth_first":
+        f |= _lib.FLAG_DEPTH_FIRST
     return f
 
 
@@ -151,8 +153,10 @@ _BACKWARD_KERNEL = "default"   # "default": one warp per 8x4 pixel block (mma.sy
                                # "tc": tcgen05 / TMEM kernel, one CTA per 16x8 pixel group (C = 32 precomputed colours)
 _STAGING = "cp_async"          # how the tile-per-CTA fp32 forward gathers a batch into shared memory: "cp_async" (16-byte LDGSTS
                                # pieces) or "tma" (one cp.async.bulk per row completing on an mbarrier; opt-in until measured)
-_BINNING = "radix"             # "radix": duplicate keys + global LSD radix sort + range detection; "tile_sort": per-tile counts ->
-                               # scan -> scatter -> one CTA per tile sorts its segment (csrc/tile_sort.cu; opt-in until measured)
+_BINNING = "depth_first"       # "depth_first" (default): Gaussians sorted by depth, instances emitted in that order, one stable sort on
+                               # the tile bits; "radix": the reference's scheme -- global LSD radix sort of the duplicated tile|depth
+                               # keys; "tile_sort": per-tile counts -> scan -> scatter -> one CTA per tile sorts its segment
+                               # (measured slower, round 2).  All three leave bit-identical binning state.
 _SPECULATIVE_BINNING = True
 # (device index, P, W, H) -> largest instance count seen so far: the next forward of that shape asks for a binning
 # buffer 25 % larger than this BEFORE the count is known (include/sagars.h, `binning_capacity_hint`)
@@ -205,12 +209,14 @@ def set_blend_wait_event(event) -> None:
     _BLEND_WAIT_EVENT = event
 
 
-def set_binning(method: str = "radix") -> None:
-    """How the (Gaussian, tile) instances are ordered: "radix" (default: the library's global radix sort of tile|depth keys) or
-    "tile_sort" (``SAGARS_FLAG_TILE_SORT``: no global sort, every tile's segment is sorted by its own CTA).  Same results."""
+def set_binning(method: str = "depth_first") -> None:
+    """How the (Gaussian, tile) instances are ordered: "radix" (the library's global radix sort of the R duplicated tile|depth
+    keys, as the reference does with CUB), "depth_first" (``SAGARS_FLAG_DEPTH_FIRST``: sort the P Gaussians by depth, emit their
+    instances in that order, one stable sort on the tile bits) or "tile_sort" (``SAGARS_FLAG_TILE_SORT``: no global sort, every
+    tile's segment is sorted by its own CTA).  Bit-identical results."""
     global _BINNING
-    if method not in ("radix", "tile_sort"):
-        raise ValueError("method in {'radix', 'tile_sort'}")
+    if method not in ("radix", "tile_sort", "depth_first"):
+        raise ValueError("method in {'radix', 'depth_first', 'tile_sort'}")
     _BINNING = method
 
 

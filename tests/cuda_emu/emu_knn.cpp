@@ -21,9 +21,9 @@ static void sort_pairs(int n, int end_bit, uint64_t* keys_a, uint32_t* vals_a, u
     uint32_t* vout = (npass & 1) ? vals_a : vals_b;
     for (int p = 0; p < npass; p++) {
         const int shift = p * SORT_RADIX_BITS;
-        cuda_emu::launch(nblk, 256, 0, radix_hist_kernel, (const uint64_t*)kin, (const uint32_t*)nullptr, n, shift, counts.data(), nblk);
+        cuda_emu::launch(nblk, 256, 0, radix_hist_kernel<uint64_t>, (const uint64_t*)kin, (const uint32_t*)nullptr, n, shift, counts.data(), nblk);
         cuda_emu::launch(SORT_RADIX * 32 / 256, 256, 0, radix_rowscan_kernel, counts.data(), nblk, totals.data());
-        cuda_emu::launch(nblk, 256, 0, radix_scatter_kernel, (const uint64_t*)kin, (const uint32_t*)vin, kout, vout, (const uint32_t*)nullptr, n,
+        cuda_emu::launch(nblk, 256, 0, radix_scatter_kernel<uint64_t>, (const uint64_t*)kin, (const uint32_t*)vin, kout, vout, (const uint32_t*)nullptr, n,
                          shift, (const uint32_t*)counts.data(), (const uint32_t*)totals.data(), nblk);
         std::swap(kin, kout);
         std::swap(vin, vout);

@@ -26,6 +26,8 @@ def emu():
     L = C.CDLL(so)
     L.emu_binning.restype = C.c_int
     L.emu_binning.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_longlong] + [C.c_void_p] * 5
+    L.emu_binning_depth_first.restype = C.c_int
+    L.emu_binning_depth_first.argtypes = L.emu_binning.argtypes
     return L
 
 
@@ -93,5 +95,43 @@ def test_speculative_layout_of_the_default_path(emu):
         assert np.array_equal(point_offsets, o.point_offsets)          # written either way (they do not live in the binning buffer)
         if expect_written:
             assert np.array_equal(keys[:R], o.keys) and np.array_equal(vals[:R], o.point_list) and np.array_equal(ranges, o.ranges)
+        else:
+            assert np.all(keys == 0xFFFFFFFFFFFFFFFF) and np.all(vals == 0xFFFFFFFF) and not ranges.any()
+
+
+@pytest.mark.parametrize("case", [("typical", 1500, 56, 72, 2.0), ("one_tile", 200, 16, 16, 2.0), ("many_tiles", 700, 130, 250, 3.0),
+                                  ("two_sort_blocks", 1200, 32, 32, 20.0), ("odd_pass_count", 900, 64, 64, 3.0), ("two_tile_passes", 900, 272, 304, 4.0)],
+                         ids=lambda c: c[0])
+def test_emulated_depth_first_binning_reproduces_the_oracle(emu, case):
+    """SAGARS_FLAG_DEPTH_FIRST: Gaussians sorted by depth, instances emitted in that order, one stable sort on the tile bits --
+    point_offsets, point_list, the rebuilt 64-bit keys and the ranges must equal the reference's (oracle's) bit for bit, ties in
+    depth included (duplicated Gaussians below)."""
+    name, P, H, W, sigma = case
+    sc = synthetic.scene(P, H, W, 3, sigma_px=sigma)
+    g = sc.gauss
+    g.means3D[1::7] = g.means3D[0::7][: len(g.means3D[1::7])]          # exact depth ties: order must fall back to the Gaussian index
+    o = common.run_oracle(sc, 3, backward=False)
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    R = o.num_rendered
+    geo = np.zeros((P, 8), np.float32)
+    geo[:, 0:2] = o.means2D
+    tt = np.ascontiguousarray(o.tiles_touched.astype(np.uint32))
+    depths = np.ascontiguousarray(o.depths.astype(np.float32))
+    radii = np.ascontiguousarray(o.radii.astype(np.int32))
+    p = lambda a: a.ctypes.data
+    for cap, n_dev, expect_written in ((R, -1, True), (R + R // 4 + 64, R, True), (R - 1, R, False)):
+        point_offsets = np.zeros(P, np.uint32)
+        keys = np.full(cap + 1, 0xFFFFFFFFFFFFFFFF, np.uint64)
+        vals = np.full(cap + 1, 0xFFFFFFFF, np.uint32)
+        ranges = np.zeros((gx * gy, 2), np.uint32)
+        nr = np.zeros(1, np.uint32)
+        rc = emu.emu_binning_depth_first(P, p(geo), p(depths), p(tt), p(radii), gx, gy, _higher_msb(gx * gy), cap, n_dev,
+                                         p(point_offsets), p(keys), p(vals), p(ranges), p(nr))
+        assert rc == 0 and int(nr[0]) == R
+        assert np.array_equal(point_offsets, o.point_offsets)
+        if expect_written:
+            assert np.array_equal(vals[:R], o.point_list)
+            assert np.array_equal(keys[:R], o.keys)
+            assert np.array_equal(ranges, o.ranges)
         else:
             assert np.all(keys == 0xFFFFFFFFFFFFFFFF) and np.all(vals == 0xFFFFFFFF) and not ranges.any()

@@ -368,13 +368,39 @@ def test_tile_sort_binning_is_bit_identical(cfg):
         b = common.run_torch_impl("ours", sc, K, backward=True)
         b2 = common.run_torch_impl("ours", sc, K, backward=False)     # second call: the speculative-capacity path
     finally:
-        R.set_binning("radix")
+        R.set_binning()
     if name == "mid_segments":
         n = a.ranges[:, 1].astype(np.int64) - a.ranges[:, 0]
         assert n.max() > 1024
     if name == "huge_segments":
         n = a.ranges[:, 1].astype(np.int64) - a.ranges[:, 0]
         assert n.max() > 8192
+    for other in (b, b2):
+        for f in ("num_rendered", "point_offsets", "point_list", "keys", "ranges", "n_contrib", "final_T", "color"):
+            assert np.array_equal(np.asarray(getattr(a, f)), np.asarray(getattr(other, f))), f
+    ok, report = common.compare(b, a, ints=(), floats=common.GRADS, verbose=False)
+    assert ok, report
+
+
+@pytest.mark.parametrize("cfg", [("cf", 6000, 120, 168, 32, 2.0), ("base_ragged", 4000, 75, 101, 3, 2.0), ("one_tile", 300, 16, 16, 32, 2.0),
+                                 ("many_tiles", 30000, 540, 960, 3, 2.0),       # 2,040 tiles: two passes on the tile bits
+                                 ("long_lists", 20000, 32, 48, 3, 60.0), ("sparse", 200, 256, 256, 3, 1.0)], ids=lambda c: c[0])
+def test_depth_first_binning_is_bit_identical(cfg):
+    """SAGARS_FLAG_DEPTH_FIRST (Gaussians sorted by depth -> instances emitted in that order -> one stable sort on the tile bits)
+    must leave exactly the binning state of the reference-style global sort of (tile | depth) keys -- point_list, rebuilt 64-bit
+    keys, ranges, point_offsets -- and therefore identical images; exact depth ties included."""
+    from seganygaussians_b200 import rasterizer as R
+    name, P, H, W, K, sigma = cfg
+    sc = synthetic.scene(P, H, W, K, sigma_px=sigma)
+    sc.gauss.means3D[1::5] = sc.gauss.means3D[0::5][: len(sc.gauss.means3D[1::5])]     # equal depths: the order falls back to the index
+    try:
+        R.set_binning("radix")
+        a = common.run_torch_impl("ours", sc, K, backward=True)
+        R.set_binning("depth_first")
+        b = common.run_torch_impl("ours", sc, K, backward=True)
+        b2 = common.run_torch_impl("ours", sc, K, backward=False)     # second call: the speculative-capacity path
+    finally:
+        R.set_binning()
     for other in (b, b2):
         for f in ("num_rendered", "point_offsets", "point_list", "keys", "ranges", "n_contrib", "final_T", "color"):
             assert np.array_equal(np.asarray(getattr(a, f)), np.asarray(getattr(other, f))), f
