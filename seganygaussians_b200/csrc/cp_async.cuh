@@ -22,6 +22,11 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
+// 4-byte asynchronous copy (list entries prefetched many chunks ahead)
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 template <int N>

@@ -59,3 +59,13 @@ int launch_render_backward_tc(const sagars_backward_args& a, const Dims& d, Geom
 }
 
 }  // namespace sagars
+
+#if defined(SAGARS_BT_TIMELINE)
+// developer hook (only in -DSAGARS_BT_TIMELINE builds): copy and clear the kernel's phase counters
+extern "C" __attribute__((visibility("default"))) int sagars_bt_timeline_read(unsigned long long* out32)
+{
+    if (cudaMemcpyFromSymbol(out32, sagars_bt_timeline, sizeof(unsigned long long) * 32) != cudaSuccess) return 1;
+    unsigned long long z[32] = {0};
+    return cudaMemcpyToSymbol(sagars_bt_timeline, z, sizeof(z)) == cudaSuccess ? 0 : 1;
+}
+#endif

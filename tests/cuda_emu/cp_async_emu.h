@@ -29,13 +29,13 @@ inline uint32_t smem_u32(const void* p)
 
 namespace emu_async {
 
-struct Piece { void* dst; const void* src; };
+struct Piece { void* dst; const void* src; int bytes = 16; };
 inline thread_local std::deque<std::vector<Piece>> groups;      // committed cp.async groups, oldest first
 inline thread_local std::vector<Piece> open_group;              // pieces issued since the last commit
 
 inline void retire(std::vector<Piece>& g)
 {
-    for (auto& p : g) std::memcpy(p.dst, p.src, 16);
+    for (auto& p : g) std::memcpy(p.dst, p.src, (size_t)p.bytes);
     g.clear();
 }
 inline void retire_all_but(size_t keep)
@@ -67,6 +67,7 @@ inline void check_complete(MBar& b)
 }  // namespace emu_async
 
 inline void cp_async16(void* smem_dst, const void* gmem_src) { emu_async::open_group.push_back({smem_dst, gmem_src}); }
+inline void cp_async4(void* smem_dst, const void* gmem_src) { emu_async::open_group.push_back({smem_dst, gmem_src, 4}); }
 inline void cp_async_commit()
 {
     emu_async::groups.push_back(std::move(emu_async::open_group));
