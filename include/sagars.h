@@ -264,6 +264,20 @@ SAGARS_API int sagars_knn(int32_t device, int32_t num_points, const float* point
                           int32_t num_queries, const float* queries /* [Q,3] or NULL */, int32_t K, int32_t exclude_self,
                           int64_t* idx_out, float* dist2_out, float* mean_dist2_out, void* temp, void* stream);
 
+/* Loss-side consumer of the K-feature render, fused.
+ * Replaces the tensor expression of train_contrastive_feature.py:232-254:
+ *     norm = render.norm(dim=0, p=2).mean();  up = F.interpolate(render[None], (out_h, out_w), mode='bilinear')[0];
+ *     samples = up.reshape(C, -1)[:, ray_index]
+ * forward : samples[C, num_rays] and norm_sum[0] = sum over the pixels of ||render[:, p]||_2 (the caller divides by H*W);
+ * backward: dL_dimage[C, H, W] = dL_dnorm_mean / (H W) * render / ||render[:, p]|| + the four bilinear taps of every ray
+ *           (written in full).  ray_index: flat indices into the RESIZED image (row-major), int64. */
+SAGARS_API int sagars_sample_rays_forward(int32_t device, int32_t C, int32_t H, int32_t W, int32_t out_h, int32_t out_w,
+                                          const float* image, const int64_t* ray_index, int32_t num_rays, float* samples,
+                                          float* norm_sum, void* stream);
+SAGARS_API int sagars_sample_rays_backward(int32_t device, int32_t C, int32_t H, int32_t W, int32_t out_h, int32_t out_w,
+                                           const float* image, const int64_t* ray_index, int32_t num_rays, const float* dL_dsamples,
+                                           const float* dL_dnorm_mean, float* dL_dimage, void* stream);
+
 /* Fused feature smoothing in front of the rasterizer:
  *     out_i = mean_k( F[idx[i,k]] / max(||F[idx[i,k]]||, 1e-12) ),   optionally  out_i /= (||out_i|| + 1e-9)
  * Replaces the tensor expression of scene/gaussian_model_ff.py:338-364 (`F.normalize(...)[select_idx, :].mean(dim=1)`)

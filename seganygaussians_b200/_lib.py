@@ -88,7 +88,7 @@ ABI_SYMBOLS = (
     "sagars_forward", "sagars_backward", "sagars_mark_visible",
     "sagars_geom_bytes", "sagars_image_bytes", "sagars_binning_bytes", "sagars_grad_scratch_bytes",
     "sagars_get_geom_layout", "sagars_get_image_layout", "sagars_get_binning_layout",
-    "sagars_sort_temp_bytes", "sagars_sort_pairs", "sagars_knn_temp_bytes", "sagars_knn", "sagars_smooth_forward", "sagars_smooth_backward",
+    "sagars_sort_temp_bytes", "sagars_sort_pairs", "sagars_knn_temp_bytes", "sagars_knn", "sagars_smooth_forward", "sagars_smooth_backward", "sagars_sample_rays_forward", "sagars_sample_rays_backward",
     "sagars_launch_count", "sagars_reset_launch_count",
     "sagars_profile_enable", "sagars_profile_num_stages", "sagars_profile_stage_name", "sagars_profile_read",
     "sagars_sizeof_forward_args", "sagars_sizeof_backward_args", "sagars_multimem_allreduce_f32",
@@ -146,6 +146,10 @@ def load() -> C.CDLL:
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.sagars_smooth_forward.restype = C.c_int
         lib.sagars_smooth_forward.argtypes = [C.c_int32] * 4 + [C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 3
+        lib.sagars_sample_rays_forward.restype = C.c_int
+        lib.sagars_sample_rays_forward.argtypes = [C.c_int32] * 6 + [C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 3
+        lib.sagars_sample_rays_backward.restype = C.c_int
+        lib.sagars_sample_rays_backward.argtypes = [C.c_int32] * 6 + [C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 4
         lib.sagars_smooth_backward.restype = C.c_int
         lib.sagars_smooth_backward.argtypes = [C.c_int32] * 4 + [C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 6
         lib.sagars_image_bytes.restype = C.c_size_t

@@ -4,6 +4,7 @@
 // (CF cuda_rasterizer/rasterizer_impl.cu:141-153,198-434) and the scratch carving of
 // GeometryState / ImageState / BinningState (rasterizer_impl.cu:155-194).
 #include "common.cuh"
+#include <sched.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -301,8 +302,14 @@ int sagars_forward(const sagars_forward_args* a,
         if (sync_mode() == 1) {
             SAGARS_CUDA(cudaStreamSynchronize(s));
         } else {
+            // poll briefly (the count is usually there within a few microseconds), then yield the core between polls: one
+            // process per GPU plus data-loader workers should not pin a core per rank on this wait
             cudaError_t q;
-            while ((q = cudaEventQuery(ev)) == cudaErrorNotReady) {}
+            unsigned spins = 0;
+            while ((q = cudaEventQuery(ev)) == cudaErrorNotReady) {
+                if (++spins > 2000) sched_yield();
+                else __builtin_ia32_pause();
+            }
             SAGARS_CUDA(q);
         }
         if (pin[0] != 0) {
@@ -569,6 +576,33 @@ int sagars_smooth_backward(int32_t device, int32_t P, int32_t C, int32_t Ks, con
     SAGARS_CUDA(cudaSetDevice(device));
     return launch_smooth_backward(P, C, Ks, features, (const long long*)nbr_idx, normalize_out, mean_norm, out,
                                   dL_dout, dL_dn_scratch, dL_dfeatures, (cudaStream_t)stream);
+}
+
+int sagars_sample_rays_forward(int32_t device, int32_t C, int32_t H, int32_t W, int32_t out_h, int32_t out_w, const float* image,
+                               const int64_t* ray_index, int32_t num_rays, float* samples, float* norm_sum, void* stream)
+{
+    g_err[0] = 0;
+    if (C < 1 || H < 1 || W < 1 || out_h < 1 || out_w < 1 || num_rays < 0 || !image || !norm_sum || (num_rays > 0 && (!ray_index || !samples))) {
+        set_error("sagars_sample_rays_forward: bad argument");
+        return SAGARS_EINVAL;
+    }
+    SAGARS_CUDA(cudaSetDevice(device));
+    return launch_sample_rays_forward(C, H, W, out_h, out_w, image, (const long long*)ray_index, num_rays, samples, norm_sum, (cudaStream_t)stream);
+}
+
+int sagars_sample_rays_backward(int32_t device, int32_t C, int32_t H, int32_t W, int32_t out_h, int32_t out_w, const float* image,
+                                const int64_t* ray_index, int32_t num_rays, const float* dL_dsamples, const float* dL_dnorm_mean,
+                                float* dL_dimage, void* stream)
+{
+    g_err[0] = 0;
+    if (C < 1 || H < 1 || W < 1 || out_h < 1 || out_w < 1 || num_rays < 0 || !image || !dL_dnorm_mean || !dL_dimage ||
+        (num_rays > 0 && (!ray_index || !dL_dsamples))) {
+        set_error("sagars_sample_rays_backward: bad argument");
+        return SAGARS_EINVAL;
+    }
+    SAGARS_CUDA(cudaSetDevice(device));
+    return launch_sample_rays_backward(C, H, W, out_h, out_w, image, (const long long*)ray_index, num_rays, dL_dsamples, dL_dnorm_mean,
+                                       dL_dimage, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <atomic>
 #include "../../include/sagars.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -200,6 +201,15 @@ void count_launch(int n = 1);
         if (_e != cudaSuccess) return ::sagars::cuda_fail(_e, #call, __FILE__, __LINE__); \
     } while (0)
 
+// "has this kernel's attribute opt-in been done on the current device?"  One atomic word per template instantiation (bit = device
+// ordinal; ordinals >= 64 simply repeat the idempotent cudaFuncSetAttribute calls): the forward thread and autograd's backward
+// thread may ask at the same time.
+struct DeviceOnce {
+    std::atomic<uint64_t> mask{0};
+    bool need(int dev) const { return dev >= 64 || !((mask.load(std::memory_order_acquire) >> dev) & 1ull); }
+    void done(int dev) { if (dev < 64) mask.fetch_or(1ull << dev, std::memory_order_release); }
+};
+
 // after a kernel launch: always check the launch; in debug mode also synchronise and check execution
 #define SAGARS_LAUNCH_CHECK(stream, debug)                                        \
     do {                                                                          \
@@ -247,6 +257,10 @@ int launch_smooth_forward(int P, int C, int Ks, const float* F, const long long*
 int launch_smooth_backward(int P, int C, int Ks, const float* F, const long long* idx, int normalize_out,
                            const float* mean_norm, const float* out, const float* dL_dout, float* dL_dn, float* dL_dF,
                            cudaStream_t s);
+int launch_sample_rays_forward(int C, int H, int W, int h, int w, const float* img, const long long* rays, int S, float* out,
+                               float* norm_sum, cudaStream_t s);
+int launch_sample_rays_backward(int C, int H, int W, int h, int w, const float* img, const long long* rays, int S, const float* g_out,
+                                const float* g_norm, float* grad_img, cudaStream_t s);
 size_t knn_temp_bytes(size_t n);
 int launch_knn(int n, const float* points, int nq, const float* queries, int K, bool exclude_self, long long* idx_out,
                float* dist_out, float* mean_out, void* temp, cudaStream_t s);

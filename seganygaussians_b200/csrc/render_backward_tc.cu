@@ -42,13 +42,13 @@ int launch_render_backward_tc(const sagars_backward_args& a, const Dims& d, Geom
     auto kern = render_backward_tc_kernel;
     const size_t smem = sizeof(BtSmem) + 1024;
     {   // opt in to the dynamic shared-memory size once per device
-        static uint64_t done_mask = 0;
+        static DeviceOnce once;
         int dev = 0;
         SAGARS_CUDA(cudaGetDevice(&dev));
-        if (!((done_mask >> (dev & 63)) & 1ull)) {
+        if (once.need(dev)) {
             SAGARS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             SAGARS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            done_mask |= 1ull << (dev & 63);
+            once.done(dev);
         }
     }
     dim3 grid(d.tiles_x, 2 * d.tiles_y);

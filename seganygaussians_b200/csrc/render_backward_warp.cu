@@ -35,13 +35,13 @@ static int launch_bwd_warp_t(const sagars_backward_args& a, const Dims& d, GeomV
     auto kern = render_backward_warp_kernel<NQ, VEC, MD, COLOR>;
     const size_t smem = sizeof(BwSmem<NQ>);
     {   // opt in to the dynamic shared-memory size once per device (not on every launch: the call takes the context lock)
-        static uint64_t done_mask = 0;
+        static DeviceOnce once;
         int dev = 0;
         SAGARS_CUDA(cudaGetDevice(&dev));
-        if (!((done_mask >> (dev & 63)) & 1ull)) {
+        if (once.need(dev)) {
             SAGARS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             SAGARS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            done_mask |= 1ull << (dev & 63);
+            once.done(dev);
         }
     }
     dim3 grid(2 * d.tiles_x, 4 * d.tiles_y);

@@ -54,12 +54,12 @@ int launch_tile_sort(int num_tiles, uint2* ranges, uint64_t* pairs, uint32_t* po
                      const uint32_t* n_dev, int cap, cudaStream_t s, bool debug)
 {
     {   // opt in to 64 KB of dynamic shared memory once per device
-        static uint64_t done_mask = 0;
+        static DeviceOnce once;
         int dev = 0;
         SAGARS_CUDA(cudaGetDevice(&dev));
-        if (!((done_mask >> (dev & 63)) & 1ull)) {
+        if (once.need(dev)) {
             SAGARS_CUDA(cudaFuncSetAttribute(tile_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TSORT_LARGE * 8)));
-            done_mask |= 1ull << (dev & 63);
+            once.done(dev);
         }
     }
     tile_sort_small_kernel<<<num_tiles, 256, 0, s>>>(ranges, pairs, point_list, keys, queue, n_dev, cap);

@@ -55,7 +55,10 @@ def _f32(t: Optional[torch.Tensor], device) -> Optional[torch.Tensor]:
         return None
     if t.device != device or t.dtype != torch.float32:
         t = t.to(device=device, dtype=torch.float32)
-    return t.contiguous()
+    t = t.contiguous()
+    if t.data_ptr() % 16:       # the kernels read rows as float4 / 16-byte async copies: a contiguous VIEW at an odd storage offset
+        t = t.clone()           # (e.g. a slice of a flat parameter buffer) gets its own 256-byte-aligned allocation
+    return t
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -267,6 +270,17 @@ def _forward_impl(settings, variant_flags, default_channels, means3D, sh, colors
     M = 0
     if sh_c is not None:
         M = int(sh_c.shape[1])
+    # cheap shape checks: a short tensor must become an error here, not an out-of-bounds read on the device
+    for name, t, n in (("opacities", opac_c, P), ("mask", mask_c, P), ("scales", scales_c, 3 * P), ("rotations", rots_c, 4 * P),
+                       ("cov3D_precomp", cov_c, 6 * P), ("shs", sh_c, 3 * M * P)):
+        if t is not None and t.numel() != n:
+            raise RuntimeError(f"{name} has {t.numel()} elements, expected {n} for {P} points")
+    if opac_c is None:
+        raise RuntimeError("opacities must have dimensions (num_points, 1)")
+    if has_md and mask_c is None:
+        raise RuntimeError("mask must have dimensions (num_points,)")
+    if sh_c is not None and (int(settings.sh_degree) + 1) ** 2 > M:
+        raise RuntimeError(f"sh_degree {int(settings.sh_degree)} needs {(int(settings.sh_degree) + 1) ** 2} coefficients, shs has {M}")
     if bg_c is None or bg_c.numel() < (1 if mask_only else num_ch):
         raise RuntimeError(f"bg must hold at least {num_ch} floats")
 
@@ -289,6 +303,7 @@ def _forward_impl(settings, variant_flags, default_channels, means3D, sh, colors
         a = _lib.ForwardArgs()
         a.device = device.index if device.index is not None else torch.cuda.current_device()
         a.flags = _flags(settings, variant_flags)
+        _TLS.last_flags = int(a.flags)       # the matching backward reuses exactly these (set_* calls in between must not split a pair)
         a.P, a.D, a.M, a.num_channels = P, int(settings.sh_degree), M, num_ch
         a.width, a.height = W, H
         a.tan_fovx, a.tan_fovy = float(settings.tanfovx), float(settings.tanfovy)
@@ -342,8 +357,9 @@ def _forward_impl(settings, variant_flags, default_channels, means3D, sh, colors
 
 
 def _backward_impl(settings, variant_flags, num_ch, num_rendered, means3D, radii, colors_precomp, mask, scales,
-                   rotations, cov3Ds_precomp, sh, geom, binning, img, grad_out_color, grad_out_mask):
-    """Shared backward: returns dict of gradient tensors (reference shapes, CF rasterize_points.cu:151-159)."""
+                   rotations, cov3Ds_precomp, sh, geom, binning, img, grad_out_color, grad_out_mask, flags=None):
+    """Shared backward: returns dict of gradient tensors (reference shapes, CF rasterize_points.cu:151-159).
+    `flags`: the flags the matching forward ran with (None: current module settings)."""
     lib = _lib.load()
     device = means3D.device
     P = int(means3D.shape[0])
@@ -375,14 +391,17 @@ def _backward_impl(settings, variant_flags, num_ch, num_rendered, means3D, radii
             return dict(means2D=z(0, 3), colors=z(0, num_ch), opacity=z(0, 1), mask=z(0, 1), means3D=z(0, 3),
                         cov3D=z(0, 6), sh=z(0, M, 3), scales=z(0, 3), rotations=z(0, 4))
         e = lambda *s: torch.empty(s, **opts)
-        g = dict(means2D=e(P, 3), colors=e(P, num_ch), opacity=e(P, 1), means3D=e(P, 3), cov3D=e(P, 6),
-                 sh=e(P, M, 3), scales=e(P, 3), rotations=e(P, 4))
+        if mask_only:   # the only gradient of the mask-only path is dL_dmask (DEPTH __init__.py:280-289): nothing else is allocated
+            g = dict(means2D=None, colors=None, opacity=None, means3D=None, cov3D=None, sh=None, scales=None, rotations=None)
+        else:
+            g = dict(means2D=e(P, 3), colors=e(P, num_ch), opacity=e(P, 1), means3D=e(P, 3), cov3D=e(P, 6),
+                     sh=e(P, M, 3), scales=e(P, 3), rotations=e(P, 4))
         g["mask"] = e(P, 1) if has_md else None
         scratch = torch.empty(int(lib.sagars_grad_scratch_bytes(P)), dtype=torch.uint8, device=device)
 
         a = _lib.BackwardArgs()
         a.device = device.index if device.index is not None else torch.cuda.current_device()
-        a.flags = _flags(settings, variant_flags)
+        a.flags = int(flags) if flags is not None else _flags(settings, variant_flags)
         a.P, a.D, a.M, a.R = P, int(settings.sh_degree), M, int(num_rendered)
         a.num_channels = num_ch
         a.width, a.height = W, H
@@ -412,13 +431,10 @@ def _backward_impl(settings, variant_flags, num_ch, num_rendered, means3D, radii
         a.dL_dmask = _ptr(g["mask"])
         a.dL_dmeans3D = _ptr(g["means3D"])
         a.dL_dcov3D = _ptr(g["cov3D"])
-        a.dL_dsh = _ptr(g["sh"]) if M > 0 else None
+        a.dL_dsh = _ptr(g["sh"]) if (M > 0 and not mask_only) else None
         a.dL_dscales = _ptr(g["scales"])
         a.dL_drotations = _ptr(g["rotations"])
         _lib.check(lib.sagars_backward(C.byref(a), _stream_ptr(device)))
-        if mask_only:
-            for k in ("means2D", "colors", "opacity", "means3D", "cov3D", "sh", "scales", "rotations"):
-                g[k] = None
     return g
 
 
@@ -446,6 +462,7 @@ def _make_rasterize_function(default_channels: int):
                 out = _forward_impl(raster_settings, 0, default_channels, *args)
             num_rendered, color, _, _, radii, geom, binning, img, num_ch = out
             ctx.raster_settings = raster_settings
+            ctx.sagars_flags = getattr(_TLS, "last_flags", None)
             ctx.num_rendered = num_rendered
             ctx.num_ch = num_ch
             ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning, img)
@@ -457,7 +474,8 @@ def _make_rasterize_function(default_channels: int):
             rs = ctx.raster_settings
             colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning, img = ctx.saved_tensors
             call = lambda: _backward_impl(rs, 0, ctx.num_ch, ctx.num_rendered, means3D, radii, colors_precomp, None,
-                                          scales, rotations, cov3Ds_precomp, sh, geom, binning, img, grad_out_color, None)
+                                          scales, rotations, cov3Ds_precomp, sh, geom, binning, img, grad_out_color, None,
+                                          flags=ctx.sagars_flags)
             if rs.debug:
                 cpu_args = cpu_deep_copy_tuple((rs.bg, means3D, radii, colors_precomp, scales, rotations, cov3Ds_precomp,
                                                 grad_out_color, sh, geom, binning, img))
@@ -495,6 +513,7 @@ class _RasterizeGaussiansDepth(torch.autograd.Function):
             out = _forward_impl(raster_settings, _lib.FLAG_MASK_DEPTH, 3, *args)
         num_rendered, color, out_mask, out_depth, radii, geom, binning, img, num_ch = out
         ctx.raster_settings = raster_settings
+        ctx.sagars_flags = getattr(_TLS, "last_flags", None)
         ctx.num_rendered = num_rendered
         ctx.num_ch = num_ch
         ctx.mask_shape = tuple(mask.shape)
@@ -508,7 +527,7 @@ class _RasterizeGaussiansDepth(torch.autograd.Function):
         colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning, img = ctx.saved_tensors
         call = lambda: _backward_impl(rs, _lib.FLAG_MASK_DEPTH, ctx.num_ch, ctx.num_rendered, means3D, radii,
                                       colors_precomp, None, scales, rotations, cov3Ds_precomp, sh, geom, binning, img,
-                                      grad_out_color, grad_out_mask)
+                                      grad_out_color, grad_out_mask, flags=ctx.sagars_flags)
         if rs.debug:
             cpu_args = cpu_deep_copy_tuple((rs.bg, means3D, radii, colors_precomp, scales, rotations, cov3Ds_precomp,
                                             grad_out_color, grad_out_mask, sh, geom, binning, img))
@@ -535,6 +554,7 @@ class _RasterizeMaskGaussians(torch.autograd.Function):
                             rotations, cov3Ds_precomp)
         num_rendered, _, out_mask, _, radii, geom, binning, img, num_ch = out
         ctx.raster_settings = raster_settings
+        ctx.sagars_flags = getattr(_TLS, "last_flags", None)
         ctx.num_rendered = num_rendered
         ctx.num_ch = num_ch
         ctx.mask_shape = tuple(mask.shape)
@@ -547,7 +567,7 @@ class _RasterizeMaskGaussians(torch.autograd.Function):
         rs = ctx.raster_settings
         means3D, means2D, scales, rotations, cov3Ds_precomp, radii, geom, binning, img = ctx.saved_tensors
         g = _backward_impl(rs, _lib.FLAG_MASK_ONLY, ctx.num_ch, ctx.num_rendered, means3D, radii, None, None, scales,
-                           rotations, cov3Ds_precomp, None, geom, binning, img, None, grad_out_mask)
+                           rotations, cov3Ds_precomp, None, geom, binning, img, None, grad_out_mask, flags=ctx.sagars_flags)
         grad_mask = g["mask"].reshape(ctx.mask_shape)
         z = lambda t: torch.zeros_like(t, dtype=torch.float32, device=grad_mask.device)
         return (z(means3D), z(means2D), z(grad_mask), grad_mask, z(scales), z(rotations), z(cov3Ds_precomp), None)

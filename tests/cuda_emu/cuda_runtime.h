@@ -182,6 +182,19 @@ template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned delta)
     return cuda_emu::shfl_from(v, lane - (int)delta >= 0 ? lane - (int)delta : lane);
 }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline float atomicAdd(float* p, float v)
+{
+    unsigned int* u = reinterpret_cast<unsigned int*>(p);
+    unsigned int o = __atomic_load_n(u, __ATOMIC_RELAXED), w;
+    float old, want;
+    do {
+        std::memcpy(&old, &o, 4);
+        want = old + v;
+        std::memcpy(&w, &want, 4);
+    } while (!__atomic_compare_exchange_n(u, &o, w, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+    std::memcpy(&old, &o, 4);
+    return old;
+}
 inline unsigned atomicMax(unsigned* p, unsigned v)
 {
     unsigned old = __atomic_load_n(p, __ATOMIC_RELAXED);

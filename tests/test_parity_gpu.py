@@ -90,6 +90,30 @@ def test_cuda_matches_live_reference(cfg):
             assert np.array_equal(ours.color, ref.color)
 
 
+# BASELINE.json configs[2] / [3] / [4] at their full sizes, default kernels only (the small LIVE_REF cases above also run the fp32 SIMT
+# path): c3-like = SYN(5M, 1036x1600, K=32) -- the garden run's size; c4 = SYN(3M, 1080x1920, K=32) (one of its 8 cameras);
+# c5-like = the depth rasterizer on SYN(2M, 1600x1600) with SH degree 3 and a per-Gaussian mask (get_scale.py's workload).
+LIVE_REF_LARGE = [("c3_like_5M", 5_000_000, 1036, 1600, 32, False, False), ("c4_3M", 3_000_000, 1080, 1920, 32, False, False),
+                  ("c5_like_depth_sh3", 2_000_000, 1600, 1600, 3, True, True)]
+
+
+@pytest.mark.parametrize("cfg", LIVE_REF_LARGE, ids=[c[0] for c in LIVE_REF_LARGE])
+def test_cuda_matches_live_reference_at_baseline_sizes(cfg):
+    """Integer state exact, final_T bit-equal, images and all gradients within 1e-4 of the unmodified reference extension."""
+    _, P, H, W, K, depth, use_sh = cfg
+    if not common.have_ref(common.variant_of(K, depth)):
+        pytest.skip("oracle/_ref not built (python oracle/build_ref.py where /root/reference is mounted)")
+    sc = synthetic.scene(P, H, W, K, sh_coeffs=16 if use_sh else 0)
+    kw = dict(depth=depth, use_sh=use_sh, sh_degree=3 if use_sh else 0)
+    ref = common.run_torch_impl("ref", sc, K, **kw)
+    torch.cuda.empty_cache()
+    ours = common.run_torch_impl("ours", sc, K, **kw)
+    ok, lines = common.compare(ours, ref, floats=common.FLOAT_FWD + common.GRADS + ("means2D", "conic_opacity", "depths", "cov3D"), verbose=False)
+    assert ok, "\n".join(lines)
+    assert np.array_equal(ours.final_T, ref.final_T)
+    assert ours.num_rendered == ref.num_rendered and ours.num_rendered > 2 * P // 3
+
+
 def _render(sc, K, colors=None, bg=None, opac=None, cov_precomp=None, use_cub=False, debug=False, backward=False, dL=None,
             tensor_cores=True):
     from seganygaussians_b200 import rasterizer as R

@@ -37,7 +37,7 @@ def _load_bindings():
         sys.path.insert(0, p)
     for name in ("gaussian_renderer", "scene", "utils", "arguments"):
         mod = sys.modules.get(name)
-        if mod is not None and not os.path.realpath(getattr(mod, "__file__", "")).startswith(os.path.realpath(common.REF_DIR)):
+        if mod is not None and not os.path.realpath(getattr(mod, "__file__", None) or "/").startswith(os.path.realpath(common.REF_DIR)):
             for k in [k for k in sys.modules if k == name or k.startswith(name + ".")]:
                 del sys.modules[k]
     ref = importlib.import_module("gaussian_renderer")
