@@ -81,8 +81,8 @@ def parse():
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region, read through NVML (the quantities
     `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` prints; B200_PROFILING.md recipe).
-    Samples are taken explicitly from the launching thread at 25 / 50 / 75 % of the timed steps: the launching thread runs
-    several steps ahead of the GPU, so the GPU is busy with queued steps while NVML is read and the read costs no GPU time.
+    Samples are taken explicitly from the launching thread right after the last timed step has been launched, while the GPU
+    is still executing the last two timed steps (the launch loop keeps a two-step lead), so the read costs no GPU time.
     A polling child / thread is deliberately NOT used: `nvidia-smi -lms 50` was measured to slow this launch-heavy step 3x
     and a 100 ms NVML thread still added up to ~1 ms/step of jitter, which would falsify the number it guards."""
 
@@ -254,15 +254,25 @@ class Runner:
     def timed(self, fn, steps, sampler=None):
         self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        marks = {steps // 4, steps // 2, (3 * steps) // 4} if sampler is not None and steps >= 8 else ({steps - 1} if sampler is not None else set())
+        # The launching thread may run at most two steps ahead of the GPU: far enough that the GPU never waits for a launch, close
+        # enough that the caching allocator keeps recycling the same scratch blocks.  NVML is read AFTER the last launch, while the
+        # GPU still executes the last two timed steps (an NVML call takes milliseconds: in the middle of the loop it drained the
+        # two-step lead and idled the GPU -- measured as `value` > `e2e`).
+        lead = []
         e0.record()
         for i in range(steps):
             fn()
-            if i in marks:
-                sampler.sample()          # the GPU is still executing queued steps
+            ev = torch.cuda.Event()
+            ev.record()
+            lead.append(ev)
+            if len(lead) > 2:
+                lead.pop(0).synchronize()
         if self.reducer is not None:
             self.reducer.wait()           # the last exchange belongs to the timed region
         e1.record()
+        if sampler is not None:
+            sampler.sample()              # the GPU is still executing timed steps
+            sampler.sample()
         self.barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
         if self.use_dist:

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SAGARS_ABI_VERSION 3
+#define SAGARS_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define SAGARS_API __attribute__((visibility("default")))

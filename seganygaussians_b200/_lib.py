@@ -15,7 +15,7 @@ _DEFAULT_LIB_PATH = os.path.join(_HERE, "lib", "libsagars.so")
 # SAGARS_LIBRARY: developer switch to load a differently built libsagars.so (a build variant under lib/variants/); never a fallback
 LIB_PATH = os.environ.get("SAGARS_LIBRARY") or _DEFAULT_LIB_PATH
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # flags (include/sagars.h)
 FLAG_PREFILTERED = 1

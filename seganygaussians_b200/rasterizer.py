@@ -275,9 +275,9 @@ def _forward_impl(settings, variant_flags, default_channels, means3D, sh, colors
                        ("cov3D_precomp", cov_c, 6 * P), ("shs", sh_c, 3 * M * P)):
         if t is not None and t.numel() != n:
             raise RuntimeError(f"{name} has {t.numel()} elements, expected {n} for {P} points")
-    if opac_c is None:
+    if P > 0 and opac_c is None:
         raise RuntimeError("opacities must have dimensions (num_points, 1)")
-    if has_md and mask_c is None:
+    if P > 0 and has_md and mask_c is None:
         raise RuntimeError("mask must have dimensions (num_points,)")
     if sh_c is not None and (int(settings.sh_degree) + 1) ** 2 > M:
         raise RuntimeError(f"sh_degree {int(settings.sh_degree)} needs {(int(settings.sh_degree) + 1) ** 2} coefficients, shs has {M}")
