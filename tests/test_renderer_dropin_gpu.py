@@ -23,6 +23,19 @@ ROOT = common.ROOT
 REF_RENDERER = os.path.join(common.REF_DIR, "renderer")
 
 
+@pytest.fixture(autouse=True)
+def _restore_import_state():
+    """The reference's python packages are put in front of sys.path for these tests only: afterwards the path entry and the
+    modules imported from it are removed again (other tests import the DROP-IN ``gaussian_renderer`` by that same name)."""
+    saved_path = list(sys.path)
+    yield
+    sys.path[:] = saved_path
+    for k in [k for k in list(sys.modules) if k.split(".")[0] in ("gaussian_renderer", "scene", "utils", "arguments")]:
+        f = getattr(sys.modules[k], "__file__", None) or ""
+        if os.path.realpath(f).startswith(os.path.realpath(common.REF_DIR)) or not f:
+            del sys.modules[k]
+
+
 def _load_bindings():
     """(reference gaussian_renderer bound to the reference extensions, our drop-in bound to libsagars)."""
     if not (os.path.exists(os.path.join(REF_RENDERER, "gaussian_renderer", "__init__.py")) and
@@ -59,7 +72,8 @@ class _Model:
         self._xyz, self._opacity, self._scaling, self._rotation = leaf(g.means3D), leaf(g.opacities), leaf(g.scales), leaf(g.rotations)
         gen = torch.Generator().manual_seed(5)
         self._sh = leaf(torch.randn(sc.P, (sh_degree + 1) ** 2, 3, generator=gen) * 0.3)
-        self._mask = leaf(torch.rand(sc.P, generator=gen) * 0.5 + 0.5)
+        # [P, 1]: the reference's depth rasterizer returns dL_dmask as [P, 1], which autograd only accepts for a mask of that shape
+        self._mask = leaf(torch.rand(sc.P, 1, generator=gen) * 0.5 + 0.5)
         self._point_features = leaf(torch.nn.functional.normalize(torch.randn(sc.P, K, generator=gen), dim=1))
         self.active_sh_degree = self.max_sh_degree = sh_degree
 
