@@ -297,15 +297,13 @@ render_backward_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
             if (!list_done) {
                 const bool more = chunk < nchunk;
                 if ((ntab > NB || (ntab == NB && more)) || !more) {
-                    if (pub <= g1 + 8) { BT_TL(21); publish(more ? NB : min(ntab, NB), !more && ntab <= NB); progress = true; BT_TL(25); }
+                    if (pub <= g1 + 8) { publish(more ? NB : min(ntab, NB), !more && ntab <= NB); progress = true; }
                 } else {
-                    BT_TL(21);
                     test_chunk();
                     progress = true;
-                    BT_TL(24);
                 }
             }
-            BT_TL(21);                     // loop overhead of the selection branch
+            if (progress) BT_TL(21);       // selection / publishing
             // (2) S = G F^T (the first one also needs the gradient rows in tensor memory)
             if (g1 < pub) {
                 int ok = 0;
@@ -451,7 +449,9 @@ render_backward_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
             }
             if (warp == 0) BT_TL(7);      // pass 2 + B3 stores
             if (have2) store_f(p, f2);                 // F[p] is free: S of batch b (its last reader) completed before this batch began
+            if (warp == 0) BT_TL(16);     // F rows -> tile
             tc::fence_smem_to_async_proxy();
+            if (warp == 0) BT_TL(17);     // proxy fence
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) {

@@ -27,8 +27,9 @@ class FeatureGradReducer:
     overlaps whatever the caller does next (the per-Gaussian geometry backward does not touch
     ``dL_dcolors`` when colours are precomputed)."""
 
-    def __init__(self, group=None, side_stream: bool = True):
+    def __init__(self, group=None, side_stream: bool = True, reduce_fn=None):
         self.group = group
+        self.reduce_fn = reduce_fn          # e.g. MulticastAllReduce.all_reduce_ (the library's own exchange); None: NCCL
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.stream = None
         self.side_stream = side_stream
@@ -39,10 +40,13 @@ class FeatureGradReducer:
             return None
         if grad.is_cuda and self.side_stream:
             if self.stream is None:
-                self.stream = torch.cuda.Stream(device=grad.device)
+                self.stream = torch.cuda.Stream(device=grad.device, priority=-1)   # ahead of queued blocks of the main stream
             self.stream.wait_stream(torch.cuda.current_stream(grad.device))
             with torch.cuda.stream(self.stream):
-                dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.group)
+                if self.reduce_fn is not None:
+                    self.reduce_fn(grad)
+                else:
+                    dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.group)
             grad.record_stream(self.stream)
             self._pending = ("stream", grad.device)
         else:
