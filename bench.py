@@ -68,7 +68,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the BASELINE configs[3] strong-scaling leg")
     ap.add_argument("--fwd-kernel", default="default", choices=["default", "tile", "warp_any"], help="developer A/B switch (rasterizer.set_blend_kernels)")
-    ap.add_argument("--bwd-kernel", default="default", choices=["default", "warp", "tile", "tc"], help="developer A/B switch")
+    ap.add_argument("--bwd-kernel", default="default", choices=["default", "tile", "tc"], help="developer A/B switch (default = the warp-per-block mma.sync kernel)")
     ap.add_argument("--allreduce-mode", default="overlap", choices=["overlap", "sync"],
                     help="N > 1: 'overlap' = the all-reduce runs on a side stream and gates only the next forward's blend stage (its "
                          "geometry stages overlap the exchange); 'sync' = the all-reduce serialises with the step")
@@ -303,7 +303,7 @@ class Runner:
 def kernel_names(a, K):
     fwd = {"default": "mma.sync warp kernel at K=32, fp32 tile kernel otherwise", "tile": "tcgen05 tile kernel",
            "warp_any": "mma.sync warp kernel for every K"}[a.fwd_kernel]
-    bwd = {"default": "library default (rasterizer.py)", "warp": "mma.sync warp kernel", "tile": "mma.sync tile kernel",
+    bwd = {"default": "mma.sync warp-per-block kernel", "tile": "mma.sync tile kernel",
            "tc": "tcgen05 / TMEM pixel-group kernel"}[a.bwd_kernel]
     return {"forward": fwd, "backward": bwd, "binning": a.binning}
 

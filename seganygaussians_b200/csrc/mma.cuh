@@ -27,6 +27,10 @@ __device__ __forceinline__ void mma_16n8k8(float* d, uint32_t a0, uint32_t a1, u
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// reciprocal without the IEEE slow path (__frcp_rn / division compile to MUFU.RCP plus a BRANCH to a denormal handler, which breaks
+// up a sequence of otherwise independent chains): one MUFU.RCP, <= 1 ulp
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 }  // namespace sagars
 
 #endif  // SAGARS_CUDA_EMU

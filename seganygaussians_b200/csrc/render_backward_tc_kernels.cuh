@@ -421,7 +421,7 @@ render_backward_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
                 const bool ok = cd && !(alpha < 1.0f / 255.0f);
                 al[j] = ok ? alpha : 0.f;
                 Gv[j] = ok ? G : 0.f;
-                rv[j] = tc::rcp_approx(1.f - al[j]);
+                rv[j] = rcp_approx(1.f - al[j]);
             }
             // B3 is free once the gradient product of the previous batch has read it (it was issued as soon as this warp and its
             // three neighbours had arrived, a whole pass 1 ago)

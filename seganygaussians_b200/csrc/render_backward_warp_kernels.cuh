@@ -109,6 +109,7 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
     __syncwarp();
 
     float T = T_final;
+    const bool any_bg = __any_sync(0xffffffffu, bgdot != 0.f);   // zero background: the term is exactly 0
     float acc_r = 0.f, last_alpha = 0.f, last_s = 0.f;
     float* const rowW = &sm.rowW[0][0];
     float* const rowQ = &sm.rowQ[0][0];
@@ -183,32 +184,37 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
             __syncwarp();
         }
         // ---- (2) thread = pixel over the group's candidates (the reference's traversal): row i of W / Q ----
-#pragma unroll 1
-        for (int i = 0; i < m; i++) {
+        //      The chain as selects (no divergent branch; a rejected pair computes on garbage and selects nothing), full groups
+        //      unrolled so that table / tile addresses are immediates.  1 / (1 - alpha) through rcp.approx (<= 1 ulp; IEEE
+        //      division costs a slow-path branch per pair); the background term is skipped when no pixel of the block has one.
+        auto one = [&](int i) {
             const float4 g0 = sm.ctab[gs + i][0];
             const float4 g1 = sm.ctab[gs + i][1];
             const float dx = g0.x - pixx, dy = g0.y - pixy;
             const float pw = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
-            const bool cd = (__float_as_int(g1.w) < my_n) && !(pw > 0.0f) && (pw >= g1.z);
             const int col = (lane + 4 * i) & 31;
-            float w = 0.f, q = 0.f;
-            if (cd) {
-                const float G = expf(pw);
-                const float alpha = fminf(0.99f, g1.y * G);
-                if (!(alpha < 1.0f / 255.0f)) {
-                    T = T / (1.f - alpha);
-                    const float s = COLOR ? rowQ[i * 32 + col] : 0.f;
-                    acc_r = last_alpha * last_s + (1.f - last_alpha) * acc_r;
-                    last_s = s;
-                    float dL_dalpha = (s - acc_r) * T;
-                    last_alpha = alpha;
-                    if (bgdot != 0.f) dL_dalpha += (-T_final / (1.f - alpha)) * bgdot;   // zero background: the term is exactly 0
-                    w = alpha * T;
-                    q = G * dL_dalpha;
-                }
-            }
-            rowW[i * 32 + col] = w;   // all lanes write: zero where the pixel did not blend
-            rowQ[i * 32 + col] = q;
+            const float G = expf(pw);
+            const float alpha = fminf(0.99f, g1.y * G);
+            const bool cd = (__float_as_int(g1.w) < my_n) && !(pw > 0.0f) && (pw >= g1.z) && !(alpha < 1.0f / 255.0f);
+            const float rcp = rcp_approx(1.f - alpha);
+            const float Tn = T * rcp;
+            const float s = COLOR ? rowQ[i * 32 + col] : 0.f;
+            const float an = last_alpha * last_s + (1.f - last_alpha) * acc_r;
+            float dL_dalpha = (s - an) * Tn;
+            if (any_bg) dL_dalpha += (-T_final * rcp) * bgdot;
+            T = cd ? Tn : T;
+            acc_r = cd ? an : acc_r;
+            last_s = cd ? s : last_s;
+            last_alpha = cd ? alpha : last_alpha;
+            rowW[i * 32 + col] = cd ? alpha * Tn : 0.f;   // all lanes write: zero where the pixel did not blend
+            rowQ[i * 32 + col] = cd ? G * dL_dalpha : 0.f;
+        };
+        if (m == BW_N) {
+#pragma unroll
+            for (int i = 0; i < BW_N; i++) one(i);
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < m; i++) one(i);
         }
         __syncwarp();
 

@@ -58,8 +58,8 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
     const int nchunk = (total + 31) >> 5;
 
     float T = 1.0f;
+    float Tc = inside ? 1.0f : 0.0f;   // 0: this pixel takes no more splats
     uint32_t last_contributor = 0;
-    bool done = !inside;
 
     float acc[2][NT][4];
 #pragma unroll
@@ -99,29 +99,37 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
             }
         }
         // ---- thread = pixel over the group's candidates (the reference's chain): w -> row i of the W tile ----
-#pragma unroll 1
-        for (int i = 0; i < FW_N; i++) {
-            float w = 0.f;
-            if (i < m) {
-                const float4 g0 = sm.ctab[gs + i][0];
-                const float4 g1 = sm.ctab[gs + i][1];
-                const float dx = g0.x - pixx, dy = g0.y - pixy;
-                const float pw = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
-                if (!done && !(pw > 0.0f) && (pw >= g1.z)) {
-                    const float alpha = fminf(0.99f, g1.y * expf(pw));
-                    if (!(alpha < 1.0f / 255.0f)) {
-                        const float test_T = T * (1 - alpha);
-                        if (test_T < 0.0001f) {
-                            done = true;
-                        } else {
-                            w = alpha * T;
-                            T = test_T;
-                            last_contributor = (uint32_t)(__float_as_int(g1.w) + 1);
-                        }
-                    }
-                }
-            }
+        // The reference's chain as selects (no divergent branch, so the chains of neighbouring candidates interleave).  Tc is the
+        // transmittance the chain tests with: it drops to 0 when the pixel saturates (or lies outside the image), after which
+        // every test_T is 0 < 1e-4 and nothing is accepted -- no separate `done` flag; T keeps the value the reference reports.
+        // A rejected pair computes on garbage (expf of a large or NaN power) and selects nothing.  Full groups (the common
+        // case) run fully unrolled: table and W-tile addresses become immediates.
+        auto one = [&](int i) {
+            const float4 g0 = sm.ctab[gs + i][0];
+            const float4 g1 = sm.ctab[gs + i][1];
+            const float dx = g0.x - pixx, dy = g0.y - pixy;
+            const float pw = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
+            const bool ok = !(pw > 0.0f) && (pw >= g1.z);
+            const float alpha = fminf(0.99f, g1.y * expf(pw));
+            const bool ok2 = ok && !(alpha < 1.0f / 255.0f);
+            const float test_T = Tc * (1 - alpha);
+            const bool low = test_T < 0.0001f;
+            const bool go = ok2 && !low;
+            const float w = go ? alpha * Tc : 0.f;
+            T = go ? test_T : T;
+            Tc = go ? test_T : ((ok2 && low) ? 0.f : Tc);
+            last_contributor = go ? (uint32_t)(__float_as_int(g1.w) + 1) : last_contributor;
             rowW[i * 32 + ((lane + 8 * i) & 31)] = w;
+        };
+        if (m == FW_N) {
+#pragma unroll
+            for (int i = 0; i < FW_N; i++) one(i);
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < FW_N; i++) {
+                if (i < m) one(i);
+                else rowW[i * 32 + ((lane + 8 * i) & 31)] = 0.f;
+            }
         }
 #pragma unroll
         for (int l = 0; l < NLD; l++) {
@@ -169,7 +177,7 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
         float4 r1_cur = __ldg(reinterpret_cast<const float4*>(geo + 8 * (size_t)id_cur + 4));
         int ntab = 0;   // candidates waiting in table slots [0, ntab)
         for (int c = 0; c < nchunk; c++) {
-            if (__all_sync(0xffffffffu, done)) { ntab = 0; break; }   // the block is saturated: nothing later can contribute
+            if (__all_sync(0xffffffffu, Tc == 0.0f)) { ntab = 0; break; }   // the block is saturated: nothing later can contribute
             // the next chunk's id, then its record, are in flight while this chunk is worked on
             const int pos_nxt = 32 * (c + 1) + lane;
             const bool has_nxt = pos_nxt < total;

@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "cp_async.cuh"
+#include "mma.cuh"      // rcp_approx
 
 namespace sagars {
 namespace tc {
@@ -111,9 +112,6 @@ __device__ __forceinline__ int ld_acquire_cta(const int* p)
     return v;
 }
 __device__ __forceinline__ void backoff(unsigned ns) { __nanosleep(ns); }
-// reciprocal without the IEEE slow path (__frcp_rn / division compile to MUFU.RCP plus a BRANCH to a denormal handler, which breaks
-// up a sequence of otherwise independent chains): one MUFU.RCP, <= 1 ulp
-__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 // wait for the phase with the given parity to complete (try_wait blocks in hardware for a bounded time per call)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)

@@ -138,7 +138,6 @@ inline bool mbar_try_wait(uint64_t* bar, uint32_t parity)
 inline bool mbar_test_wait(uint64_t* bar, uint32_t parity) { return mbar_try_wait(bar, parity); }
 inline void st_release_cta(int* p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 inline int ld_acquire_cta(const int* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
-inline float rcp_approx(float x) { return 1.0f / x; }
 inline void backoff(unsigned) { std::this_thread::sleep_for(std::chrono::microseconds(20)); }
 inline void mbar_wait(uint64_t* bar, uint32_t parity)
 {
