@@ -3,6 +3,7 @@
 #pragma once
 #include "common.cuh"
 #include "candidate.cuh"
+#include "cp_async.cuh"
 #include "mma.cuh"
 
 #ifndef SAGARS_DYNAMIC_SMEM
@@ -30,6 +31,7 @@ struct FwSmem {
     float F[FW_N][FwCfg<NQ>::RS];         // gathered feature rows (rotated, see FwCfg)
     float4 ctab[FW_TAB][2];               // candidate records (x, y, cx, cy | cz, opacity, accept_threshold, -), list order
     uint32_t cid[FW_TAB];                 // their Gaussian ids
+    float4 stage[2][32][2];               // the next chunk's records, one 32-byte slot per lane (cp.async, double buffered)
 };
 
 // NQ : float4 groups covering the K colour channels;  VEC: K % 4 == 0 -> feature rows are read as float4
@@ -75,9 +77,11 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
 
     // one group: candidates in table slots [gs, gs + m), m <= 8
     auto process_group = [&](int gs, int m) {
-        // ---- feature rows of the group: the loads are issued now and land in the F tile after the scalar loop ----
+        // ---- feature rows of the group: issued now, needed after the scalar loop.  Full float4 rows (K == ROW) are copied
+        //      straight into the F tile with cp.async (no registers held across the loop); other K go through registers ----
         constexpr int QR = ROW / 4;
         constexpr int NLD = (FW_N * QR + 31) / 32;
+        const bool direct = VEC && K == ROW;      // warp-uniform
         float4 fv[NLD];
 #pragma unroll
         for (int l = 0; l < NLD; l++) {
@@ -87,7 +91,10 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
                 const int r = idx / QR, qd = idx - r * QR;
                 const uint32_t id = sm.cid[gs + min(r, m - 1)];
                 const int c0 = 4 * qd;
-                if (VEC) {
+                if (direct) {
+                    const int qs = Cfg::ROT ? ((qd + 2 * r) & (NQE - 1)) : qd;
+                    cp_async16(Ft + r * RS + 4 * qs, features + (size_t)id * K + c0);
+                } else if (VEC) {
                     if (c0 < K) fv[l] = __ldg(reinterpret_cast<const float4*>(features + (size_t)id * K + c0));
                 } else {
                     const float* f = features + (size_t)id * K;
@@ -98,7 +105,7 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
                 }
             }
         }
-        // ---- thread = pixel over the group's candidates (the reference's chain): w -> row i of the W tile ----
+        if (direct) cp_async_commit();
         // The reference's chain as selects (no divergent branch, so the chains of neighbouring candidates interleave).  Tc is the
         // transmittance the chain tests with: it drops to 0 when the pixel saturates (or lies outside the image), after which
         // every test_T is 0 < 1e-4 and nothing is accepted -- no separate `done` flag; T keeps the value the reference reports.
@@ -131,13 +138,17 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
                 else rowW[i * 32 + ((lane + 8 * i) & 31)] = 0.f;
             }
         }
+        if (direct) {
+            cp_async_wait_all();
+        } else {
 #pragma unroll
-        for (int l = 0; l < NLD; l++) {
-            const int idx = lane + 32 * l;
-            if (idx < FW_N * QR) {
-                const int r = idx / QR, qd = idx - r * QR;
-                const int qs = Cfg::ROT ? ((qd + 2 * r) & (NQE - 1)) : qd;
-                *reinterpret_cast<float4*>(Ft + r * RS + 4 * qs) = fv[l];
+            for (int l = 0; l < NLD; l++) {
+                const int idx = lane + 32 * l;
+                if (idx < FW_N * QR) {
+                    const int r = idx / QR, qd = idx - r * QR;
+                    const int qs = Cfg::ROT ? ((qd + 2 * r) & (NQE - 1)) : qd;
+                    *reinterpret_cast<float4*>(Ft + r * RS + 4 * qs) = fv[l];
+                }
             }
         }
         __syncwarp();
@@ -171,17 +182,28 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
     };
 
     if (nchunk > 0) {
+        // list ids run two chunks ahead in registers, records one chunk ahead through a per-lane staging slot (cp.async): nothing
+        // of the next chunk occupies registers while the groups of this one are worked on
         int pos_cur = lane;
         uint32_t id_cur = pos_cur < total ? point_list[range.x + pos_cur] : 0u;
-        float4 r0_cur = __ldg(reinterpret_cast<const float4*>(geo + 8 * (size_t)id_cur));
-        float4 r1_cur = __ldg(reinterpret_cast<const float4*>(geo + 8 * (size_t)id_cur + 4));
+        cp_async16(&sm.stage[0][lane][0], geo + 8 * (size_t)id_cur);
+        cp_async16(&sm.stage[0][lane][1], geo + 8 * (size_t)id_cur + 4);
+        cp_async_commit();
+        uint32_t id_nxt = (32 + lane) < total ? point_list[range.x + 32 + lane] : 0u;
         int ntab = 0;   // candidates waiting in table slots [0, ntab)
         for (int c = 0; c < nchunk; c++) {
             if (__all_sync(0xffffffffu, Tc == 0.0f)) { ntab = 0; break; }   // the block is saturated: nothing later can contribute
-            // the next chunk's id, then its record, are in flight while this chunk is worked on
+            cp_async_wait_all();                                          // this lane's own slot: no warp barrier needed
+            const float4 r0_cur = sm.stage[c & 1][lane][0];
+            const float4 r1_cur = sm.stage[c & 1][lane][1];
             const int pos_nxt = 32 * (c + 1) + lane;
-            const bool has_nxt = pos_nxt < total;
-            const uint32_t id_nxt = has_nxt ? point_list[range.x + pos_nxt] : 0u;
+            if (c + 1 < nchunk) {                                         // warp-uniform; lanes past the end copy record 0 (ignored)
+                cp_async16(&sm.stage[(c + 1) & 1][lane][0], geo + 8 * (size_t)id_nxt);
+                cp_async16(&sm.stage[(c + 1) & 1][lane][1], geo + 8 * (size_t)id_nxt + 4);
+                cp_async_commit();
+            }
+            const int pos_nn = 32 * (c + 2) + lane;
+            const uint32_t id_nn = pos_nn < total ? point_list[range.x + pos_nn] : 0u;
 
             // block-level candidate test (candidate.cuh), lane = splat; survivors join the table in list order
             const bool keep = pos_cur < total && !block_rejects(r0_cur, r1_cur, bx0, bx1, by0, by1);
@@ -195,11 +217,6 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
                 sm.cid[slot] = id_cur;
             }
             ntab += __popc(km);
-            float4 r0_nxt = make_float4(0.f, 0.f, 0.f, 0.f), r1_nxt = r0_nxt;
-            if (has_nxt) {
-                r0_nxt = __ldg(reinterpret_cast<const float4*>(geo + 8 * (size_t)id_nxt));
-                r1_nxt = __ldg(reinterpret_cast<const float4*>(geo + 8 * (size_t)id_nxt + 4));
-            }
             __syncwarp();
 
             // full groups now, the rest is carried over (the last chunk flushes everything)
@@ -223,8 +240,7 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
 
             pos_cur = pos_nxt;
             id_cur = id_nxt;
-            r0_cur = r0_nxt;
-            r1_cur = r1_nxt;
+            id_nxt = id_nn;
         }
         // an early exit can leave carried candidates behind: the saturated block ignores them (they come later in the list)
         (void)ntab;
