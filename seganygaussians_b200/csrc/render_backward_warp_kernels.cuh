@@ -25,7 +25,11 @@ struct BwCfg {
 
 template <int NQ>
 struct BwSmem {
-    float Gs[32][BwCfg<NQ>::ROW];   // gradient row of block pixel p (= lane); quad q lives at quad (q + p) % NQE
+    // Gradient tile of the block (32 pixels x ROW channels) in the order the S product's A fragments read it: element (p, c) at
+    //   i = (((c >> 3) * 2 + (p >> 4)) * 4 + ((p >> 3) & 1) + 2 * ((c >> 2) & 1)) * 32 + 4 * (p & 7) + (c & 3),   i ^= ((i >> 6) & 1) << 4
+    // so that every fragment address of BOTH products (S = G F^T reads rows = pixels, dL/dcolour^T = G^T W^T reads rows =
+    // channels) is one of two per-lane bases plus a compile-time offset, and both are free of bank conflicts.
+    float Gs[32 * BwCfg<NQ>::ROW];
     float rowW[BW_N][32];           // row r, pixel p at (p + 4 r) & 31; also holds the gathered feature rows during (1)
     float rowQ[BW_N][32];           // same layout; holds S during (2)
     float4 ctab[BW_TAB][2];         // candidate records (x, y, cx, cy | cz, opacity, accept_threshold, -), list order
@@ -90,12 +94,11 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
             if (MD && k == K) x = gmask;   // the mask gradient rides as channel K of the colour product
             gr[k] = x;
         }
+        const int wl0 = 128 * (lane >> 4) + 32 * ((lane >> 3) & 1) + 4 * (lane & 7), wl1 = wl0 ^ 16;
 #pragma unroll
-        for (int q = 0; q < NQE; q++) {
-#pragma unroll
-            for (int c = 0; c < 4; c++)
-                if (COLOR && 4 * q + c < K) bgdot += bg[4 * q + c] * gr[4 * q + c];
-            *reinterpret_cast<float4*>(&sm.Gs[lane][4 * ((q + lane) & (NQE - 1))]) = make_float4(gr[4 * q], gr[4 * q + 1], gr[4 * q + 2], gr[4 * q + 3]);
+        for (int k = 0; k < ROW; k++) {
+            if (COLOR && k < K) bgdot += bg[k] * gr[k];
+            sm.Gs[(((k >> 2) & 1) ? wl1 : wl0) + (k >> 3) * 256 + 64 * ((k >> 2) & 1) + (k & 3)] = gr[k];
         }
     }
     float4 r0_cur = __ldg(reinterpret_cast<const float4*>(geo + 8 * (size_t)id_cur));
@@ -116,6 +119,11 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
 
     // mma fragment coordinates of this lane
     const int fg = lane >> 2, ft = lane & 3;
+    // per-lane bases into the gradient tile (see BwSmem::Gs)
+    const float* const gS0 = sm.Gs + lane;
+    const float* const gS1 = sm.Gs + (lane ^ 16);
+    const float* const gD0 = sm.Gs + 64 * (fg >> 2) + 4 * ft + (fg & 3) + 16 * (fg >> 2);
+    const float* const gD1 = sm.Gs + 64 * (fg >> 2) + 4 * ft + (fg & 3) + 16 * (1 - (fg >> 2));
     const float half_W = 0.5f * (float)W, half_H = 0.5f * (float)H;   // (0.5 * W) rounded to float, as the reference
     const float bx0 = (float)blk_x0, bx1 = bx0 + 7.f, by0 = (float)blk_y0, by1 = by0 + 3.f;   // block of pixel centres
     const float bcx = bx0 + 3.5f, bcy = by0 + 1.5f;                                            // its centre
@@ -124,7 +132,7 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
     // one group: candidates in table slots [gs, gs + m), m <= 8
     auto process_group = [&](int gs, int m) {
         // ---- (1) S (32 pixels x 8) = G (32 x C) * F^T (C x 8): feature rows gathered into the W tile's storage
-        //          (row i, channel c at (c + 4 i) & 31), S written into the Q tile's storage in the Q layout ----
+        //          (B-fragment order, see the gather), S written into the Q tile's storage in the Q layout ----
         if (COLOR) {
             float sacc[2][4];
 #pragma unroll
@@ -134,10 +142,16 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
             for (int cb = 0; cb < ROW; cb += 32) {
                 if (cb > 0) __syncwarp();
                 for (int idx = lane; idx < BW_N * QR; idx += 32) {
-                    const int r = idx / QR, qd = idx - r * QR;
+                    // feature tile in B-fragment order: quad qd of candidate r at qd * 32 + 4 r (8 lanes = 8 candidates write one
+                    // 128-byte line; the fragment of k-step ks is line 2 ks [+1], word = lane)
+                    const int r = idx & (BW_N - 1), qd = idx / BW_N;
                     const uint32_t id = sm.cid[gs + min(r, m - 1)];
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     const int c0 = cb + 4 * qd;
+                    if (VEC && K == ROW) {      // full float4 rows: straight into the tile
+                        cp_async16(rowW + qd * 32 + 4 * r, features + (size_t)id * K + c0);
+                        continue;
+                    }
                     if (VEC) {
                         if (c0 < K) v = __ldg(reinterpret_cast<const float4*>(features + (size_t)id * K + c0));
                     } else {
@@ -147,24 +161,26 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
                         if (c0 + 2 < K) v.z = __ldg(f + c0 + 2);
                         if (c0 + 3 < K) v.w = __ldg(f + c0 + 3);
                     }
-                    *reinterpret_cast<float4*>(rowW + r * 32 + 4 * ((qd + r) & 7)) = v;
+                    *reinterpret_cast<float4*>(rowW + qd * 32 + 4 * r) = v;
                 }
+                if (VEC && K == ROW) { cp_async_commit(); cp_async_wait_all(); }
                 __syncwarp();
-                const float* Fr = rowW + fg * 32;
+                const float* Fr = rowW + lane;
 #pragma unroll
                 for (int ks = 0; ks < QR / 2; ks++) {
                     uint32_t bh0, bl0, bh1, bl1;
-                    split_tf32(Fr[(ks * 8 + ft + 4 * fg) & 31], bh0, bl0);
-                    split_tf32(Fr[(ks * 8 + ft + 4 + 4 * fg) & 31], bh1, bl1);
+                    split_tf32(Fr[64 * ks], bh0, bl0);
+                    split_tf32(Fr[64 * ks + 32], bh1, bl1);
                     const int ch0 = cb + ks * 8 + ft, ch1 = ch0 + 4;
 #pragma unroll
                     for (int mt = 0; mt < 2; mt++) {
                         const int p0 = 16 * mt + fg, p1 = p0 + 8;      // block pixels of fragment rows g and g + 8
                         uint32_t ah[4], al[4];
-                        split_tf32(sm.Gs[p0][4 * (((ch0 >> 2) + p0) & (NQE - 1)) + (ch0 & 3)], ah[0], al[0]);
-                        split_tf32(sm.Gs[p1][4 * (((ch0 >> 2) + p1) & (NQE - 1)) + (ch0 & 3)], ah[1], al[1]);
-                        split_tf32(sm.Gs[p0][4 * (((ch1 >> 2) + p0) & (NQE - 1)) + (ch1 & 3)], ah[2], al[2]);
-                        split_tf32(sm.Gs[p1][4 * (((ch1 >> 2) + p1) & (NQE - 1)) + (ch1 & 3)], ah[3], al[3]);
+                        const int fo = (((cb >> 3) + ks) * 2 + mt) * 128;      // (pixel 16 mt + fg [+8], channel cb + 8 ks + ft [+4])
+                        split_tf32(gS0[fo], ah[0], al[0]);
+                        split_tf32(gS0[fo + 32], ah[1], al[1]);
+                        split_tf32(gS1[fo + 64], ah[2], al[2]);
+                        split_tf32(gS1[fo + 96], ah[3], al[3]);
                         mma_16n8k8(sacc[mt], al[0], al[1], al[2], al[3], bh0, bh1);
                         mma_16n8k8(sacc[mt], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
                         mma_16n8k8(sacc[mt], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
@@ -248,11 +264,12 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
                     for (int mm = 0; mm < MT; mm++) {
                         const int cl = 16 * mm + fg, chh = cl + 8;     // channels of fragment rows g and g + 8
                         uint32_t ah[4], al[4];
-                        split_tf32(sm.Gs[r0][4 * (((cl >> 2) + r0) & (NQE - 1)) + (cl & 3)], ah[0], al[0]);
-                        split_tf32(sm.Gs[r1][4 * (((cl >> 2) + r1) & (NQE - 1)) + (cl & 3)], ah[2], al[2]);
+                        const int go = ((4 * mm + (ks >> 1)) * 4 + (ks & 1)) * 32;   // (channel 16 mm + fg, pixel 8 ks + ft [+4])
+                        split_tf32(gD0[go], ah[0], al[0]);
+                        split_tf32(gD1[go], ah[2], al[2]);
                         if (16 * mm + 8 < ROW) {
-                            split_tf32(sm.Gs[r0][4 * (((chh >> 2) + r0) & (NQE - 1)) + (chh & 3)], ah[1], al[1]);
-                            split_tf32(sm.Gs[r1][4 * (((chh >> 2) + r1) & (NQE - 1)) + (chh & 3)], ah[3], al[3]);
+                            split_tf32(gD0[go + 256], ah[1], al[1]);                 // channel + 8: next 8-channel step
+                            split_tf32(gD1[go + 256], ah[3], al[3]);
                         } else {
                             ah[1] = al[1] = ah[3] = al[3] = 0u;
                         }
