@@ -36,6 +36,45 @@ struct BwSmem {
     uint32_t cid[BW_TAB];           // their Gaussian ids
 };
 
+// Moment basis of the geometry products: B fragment values X[p][mm] of fragment column mm = lane / 4 (1, x, y, x^2, x y, y^2, 0, 0)
+// at the block-centred pixel (x, y) = (lane % 4 - 3.5 [+4], ks - 1.5): entry [lane][2 ks + (0: x, 1: x + 4)].  Multiples of 1/4,
+// exact in tf32.  A table (two 16-byte L1 hits per group) because nvcc would otherwise rematerialise these eight values from
+// threadIdx in every group (~45 instructions) rather than hold them in registers.
+__device__ const float BW_MOMENT_BASIS[32][8] = {
+    1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f,
+    1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f,
+    1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f,
+    1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f,
+    -3.5f, 0.5f, -3.5f, 0.5f, -3.5f, 0.5f, -3.5f, 0.5f,
+    -2.5f, 1.5f, -2.5f, 1.5f, -2.5f, 1.5f, -2.5f, 1.5f,
+    -1.5f, 2.5f, -1.5f, 2.5f, -1.5f, 2.5f, -1.5f, 2.5f,
+    -0.5f, 3.5f, -0.5f, 3.5f, -0.5f, 3.5f, -0.5f, 3.5f,
+    -1.5f, -1.5f, -0.5f, -0.5f, 0.5f, 0.5f, 1.5f, 1.5f,
+    -1.5f, -1.5f, -0.5f, -0.5f, 0.5f, 0.5f, 1.5f, 1.5f,
+    -1.5f, -1.5f, -0.5f, -0.5f, 0.5f, 0.5f, 1.5f, 1.5f,
+    -1.5f, -1.5f, -0.5f, -0.5f, 0.5f, 0.5f, 1.5f, 1.5f,
+    12.25f, 0.25f, 12.25f, 0.25f, 12.25f, 0.25f, 12.25f, 0.25f,
+    6.25f, 2.25f, 6.25f, 2.25f, 6.25f, 2.25f, 6.25f, 2.25f,
+    2.25f, 6.25f, 2.25f, 6.25f, 2.25f, 6.25f, 2.25f, 6.25f,
+    0.25f, 12.25f, 0.25f, 12.25f, 0.25f, 12.25f, 0.25f, 12.25f,
+    5.25f, -0.75f, 1.75f, -0.25f, -1.75f, 0.25f, -5.25f, 0.75f,
+    3.75f, -2.25f, 1.25f, -0.75f, -1.25f, 0.75f, -3.75f, 2.25f,
+    2.25f, -3.75f, 0.75f, -1.25f, -0.75f, 1.25f, -2.25f, 3.75f,
+    0.75f, -5.25f, 0.25f, -1.75f, -0.25f, 1.75f, -0.75f, 5.25f,
+    2.25f, 2.25f, 0.25f, 0.25f, 0.25f, 0.25f, 2.25f, 2.25f,
+    2.25f, 2.25f, 0.25f, 0.25f, 0.25f, 0.25f, 2.25f, 2.25f,
+    2.25f, 2.25f, 0.25f, 0.25f, 0.25f, 0.25f, 2.25f, 2.25f,
+    2.25f, 2.25f, 0.25f, 0.25f, 0.25f, 0.25f, 2.25f, 2.25f,
+    0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f,
+    0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f,
+    0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f,
+    0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f,
+    0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f,
+    0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f,
+    0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f,
+    0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f,
+};
+
 // NQ : float4 groups covering the gradient channels (K colour channels [+ 1 mask channel when MD])
 // VEC: K % 4 == 0 and no mask channel -> feature rows are read as float4
 template <int NQ, bool VEC, bool MD, bool COLOR>
@@ -243,13 +282,9 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
             // this lane's row of the tiles: column n = fg of W^T, row fg of Q; pixel p sits at column (p + 4 fg) & 31
             const float* Wr = rowW + fg * 32;
             const float* Qr = rowQ + fg * 32;
-            // moment basis X[p][mm] of fragment column mm = fg at block pixel (x, y): value = xa + (xb + xc * y) * y
-            const float x0 = (float)ft - 3.5f, x1 = x0 + 4.f;
-            const float xa0 = (fg == 0) ? 1.f : (fg == 1) ? x0 : (fg == 3) ? x0 * x0 : 0.f;
-            const float xa1 = (fg == 0) ? 1.f : (fg == 1) ? x1 : (fg == 3) ? x1 * x1 : 0.f;
-            const float xb0 = (fg == 2) ? 1.f : (fg == 4) ? x0 : 0.f;
-            const float xb1 = (fg == 2) ? 1.f : (fg == 4) ? x1 : 0.f;
-            const float xc = (fg == 5) ? 1.f : 0.f;
+            const float4 xb_lo = __ldg(reinterpret_cast<const float4*>(&BW_MOMENT_BASIS[lane][0]));
+            const float4 xb_hi = __ldg(reinterpret_cast<const float4*>(&BW_MOMENT_BASIS[lane][4]));
+            const float xv[8] = {xb_lo.x, xb_lo.y, xb_lo.z, xb_lo.w, xb_hi.x, xb_hi.y, xb_hi.z, xb_hi.w};
 #pragma unroll
             for (int ks = 0; ks < 4; ks++) {
                 const int c0 = (ks * 8 + ft + 4 * fg) & 31, c1 = (c0 + 4) & 31;
@@ -278,9 +313,7 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
                         mma_16n8k8(dc[mm], ah[0], ah[1], ah[2], ah[3], wh0, wh1);
                     }
                 }
-                const float yb = (float)ks - 1.5f;
-                const float v0 = xa0 + (xb0 + xc * yb) * yb;
-                const float v1 = xa1 + (xb1 + xc * yb) * yb;
+                const float v0 = xv[2 * ks], v1 = xv[2 * ks + 1];   // basis at pixels (ks*8 + ft, ks*8 + ft + 4)
                 mma_16n8k8(dm, ql0, 0u, ql1, 0u, __float_as_uint(v0), __float_as_uint(v1));
                 mma_16n8k8(dm, qh0, 0u, qh1, 0u, __float_as_uint(v0), __float_as_uint(v1));
             }
@@ -293,11 +326,24 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
                 if (COLOR && ch < K) red_add(dL_dcolors + (size_t)id * K + ch, v);
                 else if (MD && ch == K) red_add(ggrad + (size_t)id * GG_STRIDE + 6, v);
             };
+            if (COLOR && !MD && ROW >= 16 && K == ROW) {     // full rows (warp-uniform): one base per candidate, no per-channel bounds
+                float* const pa = dL_dcolors + (size_t)ida * K + fg;
+                float* const pb = dL_dcolors + (size_t)idb * K + fg;
+                if (va) {
 #pragma unroll
-            for (int mm = 0; mm < MT; mm++) {
-                const int cl = 16 * mm + fg;
-                if (va) { emit(ida, cl, dc[mm][0]); emit(ida, cl + 8, dc[mm][2]); }
-                if (vb) { emit(idb, cl, dc[mm][1]); emit(idb, cl + 8, dc[mm][3]); }
+                    for (int mm = 0; mm < MT; mm++) { red_add(pa + 16 * mm, dc[mm][0]); red_add(pa + 16 * mm + 8, dc[mm][2]); }
+                }
+                if (vb) {
+#pragma unroll
+                    for (int mm = 0; mm < MT; mm++) { red_add(pb + 16 * mm, dc[mm][1]); red_add(pb + 16 * mm + 8, dc[mm][3]); }
+                }
+            } else {
+#pragma unroll
+                for (int mm = 0; mm < MT; mm++) {
+                    const int cl = 16 * mm + fg;
+                    if (va) { emit(ida, cl, dc[mm][0]); emit(ida, cl + 8, dc[mm][2]); }
+                    if (vb) { emit(idb, cl, dc[mm][1]); emit(idb, cl + 8, dc[mm][3]); }
+                }
             }
         }
         // moments of row fg: (m0, mx) in lane ft = 0, (my, mxx) in ft = 1, (mxy, myy) in ft = 2 of the quad
@@ -316,23 +362,19 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
                 const float conx = g0.z, cony = g0.w, conz = g1.x, o = g1.y;
                 // sums over the pixels of q * (1, dx, dy, dx^2, dx dy, dy^2) with d = centre - pixel = c - x'
                 const float cx = g0.x - bcx, cy = g0.y - bcy;
+                // every lane evaluates all five sums and selects its two outputs: the three-way split by ft would run serially
                 const float Sx = cx * m0 - mx;
                 const float Sy = cy * m0 - my;
-                float ua, ub;
-                int sa, sb;
-                if (ft == 0) {
-                    ua = m0; sa = 5;                                                  // dL/dopacity
-                    ub = -o * half_W * (conx * Sx + cony * Sy); sb = 0;               // dL/dmean2D.x
-                } else if (ft == 1) {
-                    const float Sxx = cx * cx * m0 - 2.f * cx * mx + mxx;
-                    ua = -o * half_H * (conz * Sy + cony * Sx); sa = 1;               // dL/dmean2D.y
-                    ub = -0.5f * o * Sxx; sb = 2;                                     // dL/dconic.x
-                } else {
-                    const float Sxy = cx * cy * m0 - cx * my - cy * mx + mxy;
-                    const float Syy = cy * cy * m0 - 2.f * cy * my + myy;
-                    ua = -0.5f * o * Sxy; sa = 3;                                     // dL/dconic.y
-                    ub = -0.5f * o * Syy; sb = 4;                                     // dL/dconic.w
-                }
+                const float Sxx = cx * cx * m0 - 2.f * cx * mx + mxx;
+                const float Sxy = cx * cy * m0 - cx * my - cy * mx + mxy;
+                const float Syy = cy * cy * m0 - 2.f * cy * my + myy;
+                const float dmx = -o * half_W * (conx * Sx + cony * Sy);              // dL/dmean2D.x
+                const float dmy = -o * half_H * (conz * Sy + cony * Sx);              // dL/dmean2D.y
+                const float hno = -0.5f * o;
+                // ft = 0: (dL/dopacity -> 5, dmean2D.x -> 0); 1: (dmean2D.y -> 1, dconic.x -> 2); 2: (dconic.y -> 3, dconic.w -> 4)
+                const float ua = (ft == 0) ? m0 : (ft == 1) ? dmy : hno * Sxy;
+                const float ub = (ft == 0) ? dmx : (ft == 1) ? hno * Sxx : hno * Syy;
+                const int sa = (ft == 0) ? 5 : 2 * ft - 1, sb = 2 * ft;
                 red_add(ggrad + (size_t)id * GG_STRIDE + sa, ua);
                 red_add(ggrad + (size_t)id * GG_STRIDE + sb, ub);
             }
