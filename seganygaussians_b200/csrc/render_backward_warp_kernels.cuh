@@ -13,6 +13,7 @@
 namespace sagars {
 
 
+constexpr int BW_RS = 36;     // row stride (words) of the W / Q tiles
 constexpr int BW_N = 8;      // candidates per group = rows of the W / Q tiles = N of the colour product
 constexpr int BW_TAB = 40;   // candidate table: up to 7 carried over + 32 new
 
@@ -30,8 +31,11 @@ struct BwSmem {
     // so that every fragment address of BOTH products (S = G F^T reads rows = pixels, dL/dcolour^T = G^T W^T reads rows =
     // channels) is one of two per-lane bases plus a compile-time offset, and both are free of bank conflicts.
     float Gs[32 * BwCfg<NQ>::ROW];
-    float rowW[BW_N][32];           // row r, pixel p at (p + 4 r) & 31; also holds the gathered feature rows during (1)
-    float rowQ[BW_N][32];           // same layout; holds S during (2)
+    // W / Q tiles: candidate row r, block pixel p at r * BW_RS + p.  The row stride of 36 words makes the scalar pass (lane = pixel,
+    // row = immediate) and the fragment reads of the gradient product (lane = (candidate fg, pixel ft), 36 fg = 4 fg mod 32) both
+    // conflict-free with addresses of the form per-lane base + immediate.
+    float rowW[BW_N][BW_RS];        // also holds the gathered feature rows during (1)
+    float rowQ[BW_N][BW_RS];        // holds S during (2)
     float4 ctab[BW_TAB][2];         // candidate records (x, y, cx, cy | cz, opacity, accept_threshold, -), list order
     uint32_t cid[BW_TAB];           // their Gaussian ids
 };
@@ -146,7 +150,7 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
         float* w = &sm.rowW[0][0];
         float* q = &sm.rowQ[0][0];
 #pragma unroll
-        for (int i = 0; i < BW_N; i++) { w[i * 32 + lane] = 0.f; q[i * 32 + lane] = 0.f; }
+        for (int i = 0; i < BW_N; i++) { w[i * BW_RS + lane] = 0.f; q[i * BW_RS + lane] = 0.f; }
     }
     __syncwarp();
 
@@ -231,10 +235,10 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
 #pragma unroll
             for (int mt = 0; mt < 2; mt++) {
                 const int pa = 16 * mt + fg, pb = pa + 8;
-                rowQ[(2 * ft) * 32 + ((pa + 8 * ft) & 31)] = sacc[mt][0];
-                rowQ[(2 * ft + 1) * 32 + ((pa + 8 * ft + 4) & 31)] = sacc[mt][1];
-                rowQ[(2 * ft) * 32 + ((pb + 8 * ft) & 31)] = sacc[mt][2];
-                rowQ[(2 * ft + 1) * 32 + ((pb + 8 * ft + 4) & 31)] = sacc[mt][3];
+                rowQ[(2 * ft) * BW_RS + pa] = sacc[mt][0];
+                rowQ[(2 * ft + 1) * BW_RS + pa] = sacc[mt][1];
+                rowQ[(2 * ft) * BW_RS + pb] = sacc[mt][2];
+                rowQ[(2 * ft + 1) * BW_RS + pb] = sacc[mt][3];
             }
             __syncwarp();
         }
@@ -247,13 +251,12 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
             const float4 g1 = sm.ctab[gs + i][1];
             const float dx = g0.x - pixx, dy = g0.y - pixy;
             const float pw = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
-            const int col = (lane + 4 * i) & 31;
             const float G = expf(pw);
             const float alpha = fminf(0.99f, g1.y * G);
             const bool cd = (__float_as_int(g1.w) < my_n) && !(pw > 0.0f) && (pw >= g1.z) && !(alpha < 1.0f / 255.0f);
             const float rcp = rcp_approx(1.f - alpha);
             const float Tn = T * rcp;
-            const float s = COLOR ? rowQ[i * 32 + col] : 0.f;
+            const float s = COLOR ? rowQ[i * BW_RS + lane] : 0.f;
             const float an = last_alpha * last_s + (1.f - last_alpha) * acc_r;
             float dL_dalpha = (s - an) * Tn;
             if (any_bg) dL_dalpha += (-T_final * rcp) * bgdot;
@@ -261,8 +264,8 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
             acc_r = cd ? an : acc_r;
             last_s = cd ? s : last_s;
             last_alpha = cd ? alpha : last_alpha;
-            rowW[i * 32 + col] = cd ? alpha * Tn : 0.f;   // all lanes write: zero where the pixel did not blend
-            rowQ[i * 32 + col] = cd ? G * dL_dalpha : 0.f;
+            rowW[i * BW_RS + lane] = cd ? alpha * Tn : 0.f;   // all lanes write: zero where the pixel did not blend
+            rowQ[i * BW_RS + lane] = cd ? G * dL_dalpha : 0.f;
         };
         if (m == BW_N) {
 #pragma unroll
@@ -280,14 +283,14 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
         float dm[4] = {0.f, 0.f, 0.f, 0.f};
         {
             // this lane's row of the tiles: column n = fg of W^T, row fg of Q; pixel p sits at column (p + 4 fg) & 31
-            const float* Wr = rowW + fg * 32;
-            const float* Qr = rowQ + fg * 32;
+            const float* Wr = rowW + fg * BW_RS + ft;
+            const float* Qr = rowQ + fg * BW_RS + ft;
             const float4 xb_lo = __ldg(reinterpret_cast<const float4*>(&BW_MOMENT_BASIS[lane][0]));
             const float4 xb_hi = __ldg(reinterpret_cast<const float4*>(&BW_MOMENT_BASIS[lane][4]));
             const float xv[8] = {xb_lo.x, xb_lo.y, xb_lo.z, xb_lo.w, xb_hi.x, xb_hi.y, xb_hi.z, xb_hi.w};
 #pragma unroll
             for (int ks = 0; ks < 4; ks++) {
-                const int c0 = (ks * 8 + ft + 4 * fg) & 31, c1 = (c0 + 4) & 31;
+                const int c0 = ks * 8, c1 = c0 + 4;                      // block pixels ks*8 + ft and + 4 (ft is in the base)
                 uint32_t wh0, wl0, wh1, wl1, qh0, ql0, qh1, ql1;
                 split_tf32(Wr[c0], wh0, wl0);
                 split_tf32(Wr[c1], wh1, wl1);

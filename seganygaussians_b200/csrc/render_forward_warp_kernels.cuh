@@ -13,6 +13,7 @@
 namespace sagars {
 
 
+constexpr int FW_WS = 40;    // row stride (words) of the W tile
 constexpr int FW_N = 8;      // candidates per group = k extent of one mma step
 constexpr int FW_TAB = 40;   // candidate table: up to 7 carried over + 32 new
 
@@ -21,14 +22,16 @@ struct FwCfg {
     static constexpr int NQE = NQ < 2 ? 2 : NQ;                 // quads per feature row (power of two)
     static constexpr int ROW = 4 * NQE;                         // padded channel count
     static constexpr int NT = ROW / 8;                          // 8-channel n-tiles
-    static constexpr int RS = (ROW == 16) ? 24 : ROW;           // row stride of the feature tile (floats)
-    static constexpr bool ROT = ROW >= 32;                      // rotate row r by 8 r channels (conflict-free fragment loads)
+    // row stride of the feature tile (floats): 8 (mod 32) for ROW >= 16, so that the B-fragment reads (lane = (channel fg,
+    // candidate ft), address = ft * RS + fg + immediate) hit 32 different banks without any per-row rotation
+    static constexpr int RS = (ROW >= 16) ? ROW + 8 : ROW;
 };
 
 template <int NQ>
 struct FwSmem {
-    float rowW[FW_N][32];                 // weight of candidate r for pixel p at (p + 8 r) & 31
-    float F[FW_N][FwCfg<NQ>::RS];         // gathered feature rows (rotated, see FwCfg)
+    float rowW[FW_N][FW_WS];              // weight of candidate r for pixel p at r * FW_WS + p (stride 40 = 8 mod 32: the scalar pass
+                                          // and the A-fragment reads are both conflict-free with base + immediate addresses)
+    float F[FW_N][FwCfg<NQ>::RS];         // gathered feature rows
     float4 ctab[FW_TAB][2];               // candidate records (x, y, cx, cy | cz, opacity, accept_threshold, -), list order
     uint32_t cid[FW_TAB];                 // their Gaussian ids
     float4 stage[2][32][2];               // the next chunk's records, one 32-byte slot per lane (cp.async, double buffered)
@@ -92,8 +95,7 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
                 const uint32_t id = sm.cid[gs + min(r, m - 1)];
                 const int c0 = 4 * qd;
                 if (direct) {
-                    const int qs = Cfg::ROT ? ((qd + 2 * r) & (NQE - 1)) : qd;
-                    cp_async16(Ft + r * RS + 4 * qs, features + (size_t)id * K + c0);
+                    cp_async16(Ft + r * RS + 4 * qd, features + (size_t)id * K + c0);
                 } else if (VEC) {
                     if (c0 < K) fv[l] = __ldg(reinterpret_cast<const float4*>(features + (size_t)id * K + c0));
                 } else {
@@ -126,7 +128,7 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
             T = go ? test_T : T;
             Tc = go ? test_T : ((ok2 && low) ? 0.f : Tc);
             last_contributor = go ? (uint32_t)(__float_as_int(g1.w) + 1) : last_contributor;
-            rowW[i * 32 + ((lane + 8 * i) & 31)] = w;
+            rowW[i * FW_WS + lane] = w;
         };
         if (m == FW_N) {
 #pragma unroll
@@ -135,7 +137,7 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
 #pragma unroll 1
             for (int i = 0; i < FW_N; i++) {
                 if (i < m) one(i);
-                else rowW[i * 32 + ((lane + 8 * i) & 31)] = 0.f;
+                else rowW[i * FW_WS + lane] = 0.f;
             }
         }
         if (direct) {
@@ -146,8 +148,7 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
                 const int idx = lane + 32 * l;
                 if (idx < FW_N * QR) {
                     const int r = idx / QR, qd = idx - r * QR;
-                    const int qs = Cfg::ROT ? ((qd + 2 * r) & (NQE - 1)) : qd;
-                    *reinterpret_cast<float4*>(Ft + r * RS + 4 * qs) = fv[l];
+                    *reinterpret_cast<float4*>(Ft + r * RS + 4 * qd) = fv[l];
                 }
             }
         }
@@ -158,19 +159,18 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
         for (int mt = 0; mt < 2; mt++) {
             // a0 = (pixel 16 mt + fg, candidate ft), a1 = (pixel + 8, ft), a2 = (pixel, ft + 4), a3 = (pixel + 8, ft + 4)
             const int pa = 16 * mt + fg, pb = pa + 8;
-            split_tf32(rowW[ft * 32 + ((pa + 8 * ft) & 31)], ah[mt][0], al[mt][0]);
-            split_tf32(rowW[ft * 32 + ((pb + 8 * ft) & 31)], ah[mt][1], al[mt][1]);
-            split_tf32(rowW[(ft + 4) * 32 + ((pa + 8 * ft) & 31)], ah[mt][2], al[mt][2]);   // 8 (ft + 4) = 8 ft (mod 32)
-            split_tf32(rowW[(ft + 4) * 32 + ((pb + 8 * ft) & 31)], ah[mt][3], al[mt][3]);
+            split_tf32(rowW[ft * FW_WS + pa], ah[mt][0], al[mt][0]);
+            split_tf32(rowW[ft * FW_WS + pb], ah[mt][1], al[mt][1]);
+            split_tf32(rowW[(ft + 4) * FW_WS + pa], ah[mt][2], al[mt][2]);
+            split_tf32(rowW[(ft + 4) * FW_WS + pb], ah[mt][3], al[mt][3]);
         }
 #pragma unroll
         for (int nt = 0; nt < NT; nt++) {
             // b0 = (candidate ft, channel 8 nt + fg), b1 = (candidate ft + 4, same channel)
             const int ch = 8 * nt + fg;
-            const int c0 = Cfg::ROT ? ((ch + 8 * ft) & (ROW - 1)) : ch;
             uint32_t bh0, bl0, bh1, bl1;
-            split_tf32(Ft[ft * RS + c0], bh0, bl0);
-            split_tf32(Ft[(ft + 4) * RS + (Cfg::ROT ? ((ch + 8 * (ft + 4)) & (ROW - 1)) : ch)], bh1, bl1);
+            split_tf32(Ft[ft * RS + ch], bh0, bl0);
+            split_tf32(Ft[(ft + 4) * RS + ch], bh1, bl1);
 #pragma unroll
             for (int mt = 0; mt < 2; mt++) {
                 mma_16n8k8(acc[mt][nt], al[mt][0], al[mt][1], al[mt][2], al[mt][3], bh0, bh1);
