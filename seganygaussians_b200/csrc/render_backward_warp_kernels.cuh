@@ -156,7 +156,7 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
 
     float T = T_final;
     const bool any_bg = __any_sync(0xffffffffu, bgdot != 0.f);   // zero background: the term is exactly 0
-    float acc_r = 0.f, last_alpha = 0.f, last_s = 0.f;
+    float u = 0.f;   // see the scalar pass
     float* const rowW = &sm.rowW[0][0];
     float* const rowQ = &sm.rowQ[0][0];
 
@@ -251,21 +251,24 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
             const float4 g1 = sm.ctab[gs + i][1];
             const float dx = g0.x - pixx, dy = g0.y - pixy;
             const float pw = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
-            const float G = expf(pw);
-            const float alpha = fminf(0.99f, g1.y * G);
-            const bool cd = (__float_as_int(g1.w) < my_n) && !(pw > 0.0f) && (pw >= g1.z) && !(alpha < 1.0f / 255.0f);
-            const float rcp = rcp_approx(1.f - alpha);
+            const float G0 = expf(pw);
+            const float alpha0 = fminf(0.99f, g1.y * G0);
+            const bool cd = (__float_as_int(g1.w) < my_n) && !(pw > 0.0f) && (pw >= g1.z) && !(alpha0 < 1.0f / 255.0f);
+            // a pair that does not blend runs the same arithmetic with G = alpha = 0: u and the products then keep / produce
+            // exactly what they should (u' = 0 s + 1 u, w = 0, q = 0); only T is selected (rcp.approx(1) need not be exactly 1)
+            const float G = cd ? G0 : 0.f, alpha = cd ? alpha0 : 0.f;
+            const float oma = 1.f - alpha;
+            const float rcp = rcp_approx(oma);
             const float Tn = T * rcp;
             const float s = COLOR ? rowQ[i * BW_RS + lane] : 0.f;
-            const float an = last_alpha * last_s + (1.f - last_alpha) * acc_r;
-            float dL_dalpha = (s - an) * Tn;
+            // u = "colour behind" dotted with the pixel's gradient: the reference's accum_rec recurrence (last_alpha * last_color +
+            // (1 - last_alpha) * accum_rec) evaluated when a pair is accepted instead of when the next one is
+            float dL_dalpha = (s - u) * Tn;
             if (any_bg) dL_dalpha += (-T_final * rcp) * bgdot;
+            u = alpha * s + oma * u;
             T = cd ? Tn : T;
-            acc_r = cd ? an : acc_r;
-            last_s = cd ? s : last_s;
-            last_alpha = cd ? alpha : last_alpha;
-            rowW[i * BW_RS + lane] = cd ? alpha * Tn : 0.f;   // all lanes write: zero where the pixel did not blend
-            rowQ[i * BW_RS + lane] = cd ? G * dL_dalpha : 0.f;
+            rowW[i * BW_RS + lane] = alpha * Tn;          // all lanes write: zero where the pixel did not blend
+            rowQ[i * BW_RS + lane] = G * dL_dalpha;
         };
         if (m == BW_N) {
 #pragma unroll
@@ -392,7 +395,7 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
         const uint32_t id_nxt = pos_nxt >= 0 ? point_list[range.x + pos_nxt] : 0u;
 
         // block-level candidate test (candidate.cuh), lane = splat; survivors join the table in list order
-        const bool keep = pos_cur >= 0 && !block_rejects(r0_cur, r1_cur, bx0, bx1, by0, by1);
+        const bool keep = pos_cur >= 0 && !block_rejects<true>(r0_cur, r1_cur, bx0, bx1, by0, by1);
         const uint32_t km = __ballot_sync(0xffffffffu, keep);
         if (keep) {
             const int slot = ntab + __popc(km & lt);
