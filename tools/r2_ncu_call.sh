@@ -9,4 +9,4 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:rend
     python bench.py --steps 1 --warmup 4 --no-cpu-baseline --no-c4 > gpurun_out/r2_ncu_full_bench.log 2>&1
 echo "full capture rc=$?"
 ls -la gpurun_out/r2_render_default.ncu-rep gpurun_out/r2_final_launches_ncu.csv
-timeout 300 python bench.py --steps 200 --warmup 10 --no-c4 > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err; tail -c 600 gpurun_out/r2_bench_default.json
+true
