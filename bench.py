@@ -184,9 +184,12 @@ class Runner:
             c = synthetic.make_camera(H, W, ci)
             dev_t = [t.to(dev) for t in (c.world_view_transform, c.full_proj_transform, c.camera_center, torch.zeros(K))]
             self.rasts.append(Rast(raster_settings=self._settings(c, *dev_t)))
-            pinned = [t.clone().pin_memory() for t in (c.world_view_transform, c.full_proj_transform, c.camera_center, torch.zeros(K))]
+            # the camera as ONE pinned buffer (view 16 | projection 16 | background K | centre 3 floats; every part 16-byte aligned):
+            # one host -> device copy per step
+            pinned = torch.cat([c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1), torch.zeros(K),
+                                c.camera_center.reshape(-1)]).float().pin_memory()
             self.host_cams.append((c, pinned))
-            self.h2d_bytes += sum(t.numel() * 4 for t in pinned)
+            self.h2d_bytes += pinned.numel() * 4
         self.reducer = None
         self.own_allreduce = None
         if use_dist and a.impl == "ours":
@@ -234,10 +237,12 @@ class Runner:
             t.grad = None
         total = None
         for (c, pinned) in self.host_cams:
-            view, proj, campos, bg = (t.to(self.dev, non_blocking=True) for t in pinned)
+            cam = pinned.to(self.dev, non_blocking=True)
+            K_ = self.wl["K"]
+            view, proj, bg, campos = cam[0:16].view(4, 4), cam[16:32].view(4, 4), cam[32:32 + K_], cam[32 + K_:35 + K_]
             rast = self.Rast(raster_settings=self._settings(c, view, proj, campos, bg))
             color, radii = self._render(rast)
-            loss = (color * self.dL).sum()
+            loss = torch.dot(color.reshape(-1), self.dL.reshape(-1))   # = (color * dL).sum(), one reduction instead of two kernels
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
         if self.use_dist:

@@ -28,24 +28,24 @@ def main():
     marks = []
 
     e2e = "--e2e" in sys.argv
-    view_h, proj_h, campos_h, bg_h = (t.clone().pin_memory() for t in (c.world_view_transform, c.full_proj_transform,
-                                                                        c.camera_center, torch.zeros(K)))
+    cam_h = torch.cat([c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1), torch.zeros(K),
+                       c.camera_center.reshape(-1)]).float().pin_memory()      # bench.py's packed camera buffer
 
     def step():
         for t in leaves:
             t.grad = None
         t0 = time.perf_counter()
         if e2e:   # bench.py's end-to-end step: camera from pinned host memory, loss scalar read back
+            cam = cam_h.to(dev, non_blocking=True)
             r = R.GaussianRasterizerContrastiveF(raster_settings=rs._replace(
-                viewmatrix=view_h.to(dev, non_blocking=True), projmatrix=proj_h.to(dev, non_blocking=True),
-                campos=campos_h.to(dev, non_blocking=True), bg=bg_h.to(dev, non_blocking=True)))
+                viewmatrix=cam[0:16].view(4, 4), projmatrix=cam[16:32].view(4, 4), bg=cam[32:32 + K], campos=cam[32 + K:35 + K]))
         else:
             r = rast
         color, radii = r(means3D=means3D, means2D=means2D, opacities=opac, shs=None, colors_precomp=colors,
                          scales=scales, rotations=rots, cov3D_precomp=None)
         t1 = time.perf_counter()
         if e2e:
-            loss = (color * dL).sum()
+            loss = torch.dot(color.reshape(-1), dL.reshape(-1))
             loss.backward()
             float(loss.item())
         else:

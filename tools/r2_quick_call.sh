@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# quick check of a kernel change: parity tests (small + c2-size live reference) and the c2 bench stage times
+# quick check of a change: parity tests (small + c2-size live reference), the c2 bench stage times, the e2e kernel timeline
 set -u
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_parity_gpu.py -m gpu -q -x -k "not baseline_sizes" 2>&1 | tail -4
@@ -12,3 +12,5 @@ try:
 except Exception as e:
     print("c2: n/a", e); print(open("gpurun_out/r2_quick_c2.err").read()[-1500:])
 PY
+timeout 300 python bench.py --impl reference --steps 20 --warmup 3 --no-cpu-baseline --no-c4 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('reference arm: value ms %.2f e2e ms %.2f' % (d['ms_per_step'], d['e2e']['ms_per_step']))"
+timeout 300 python tools/gpu_timeline.py --e2e > gpurun_out/r2_e2e_timeline.txt 2>&1; tail -75 gpurun_out/r2_e2e_timeline.txt
