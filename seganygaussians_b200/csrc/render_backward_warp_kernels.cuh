@@ -231,7 +231,7 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
                 }
             }
             __syncwarp();   // the feature rows are consumed; (2) rewrites this storage row by row
-            // fragment (pixel 16 mt + fg [+8], candidates 2 ft, 2 ft + 1) -> S[i][(p + 4 i) & 31]
+            // fragment (pixel 16 mt + fg [+8], candidates 2 ft, 2 ft + 1) -> S[i][p] in the Q tile (row stride BW_RS)
 #pragma unroll
             for (int mt = 0; mt < 2; mt++) {
                 const int pa = 16 * mt + fg, pb = pa + 8;
@@ -285,7 +285,7 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
         for (int mm = 0; mm < MT; mm++) dc[mm][0] = dc[mm][1] = dc[mm][2] = dc[mm][3] = 0.f;
         float dm[4] = {0.f, 0.f, 0.f, 0.f};
         {
-            // this lane's row of the tiles: column n = fg of W^T, row fg of Q; pixel p sits at column (p + 4 fg) & 31
+            // this lane's row of the tiles: column n = fg of W^T, row fg of Q; pixel p sits at word p of the row (ft is in the base)
             const float* Wr = rowW + fg * BW_RS + ft;
             const float* Qr = rowQ + fg * BW_RS + ft;
             const float4 xb_lo = __ldg(reinterpret_cast<const float4*>(&BW_MOMENT_BASIS[lane][0]));
@@ -424,7 +424,6 @@ render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __
             const int left = ntab - gs;
             float4 a0, a1;
             uint32_t ci = 0;
-            int cp = 0;
             if (lane < left) { a0 = sm.ctab[gs + lane][0]; a1 = sm.ctab[gs + lane][1]; ci = sm.cid[gs + lane]; }
             __syncwarp();
             if (lane < left) { sm.ctab[lane][0] = a0; sm.ctab[lane][1] = a1; sm.cid[lane] = ci; }

@@ -230,7 +230,6 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
                 const int left = ntab - gs;
                 float4 a0, a1;
                 uint32_t ci = 0;
-                int cp = 0;
                 if (lane < left) { a0 = sm.ctab[gs + lane][0]; a1 = sm.ctab[gs + lane][1]; ci = sm.cid[gs + lane]; }
                 __syncwarp();
                 if (lane < left) { sm.ctab[lane][0] = a0; sm.ctab[lane][1] = a1; sm.cid[lane] = ci; }
