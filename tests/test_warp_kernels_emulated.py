@@ -25,11 +25,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # (a candidate's list position rides in the unused 8th float of its record in the warp kernels' candidate tables: measured on
 # B200 in round 2, forward 1.009 -> 0.931 ms at c2, and made the only code path)
-@pytest.fixture(scope="module", params=["default"])
+# "fw_bulk": the forward warp kernel with its feature rows fetched by bulk copies on an mbarrier (-DSAGARS_FW_BULK=1, the TMA-unit
+# variant measured against the cp.async default in round 2)
+@pytest.fixture(scope="module", params=["default", "fw_bulk"])
 def emu(request):
     d = tempfile.mkdtemp(prefix="sagars_emu_")
     so = os.path.join(d, "libemu_warp.so")
-    extra = []
+    extra = ["-DSAGARS_FW_BULK=1"] if request.param == "fw_bulk" else []
     subprocess.check_call(["g++", "-O1", "-std=c++20", "-pthread", "-ffp-contract=off", "-shared", "-fPIC"] + extra +
                           ["-I", os.path.join(ROOT, "tests", "cuda_emu"), "-I", os.path.join(ROOT, "seganygaussians_b200", "csrc"),
                            os.path.join(ROOT, "tests", "cuda_emu", "emu_warp_kernels.cpp"), "-o", so])
@@ -106,8 +108,8 @@ def test_forward_tcgen05_tile_kernel(emu, case):
     """The opt-in tile-per-CTA forward on tcgen05 (SAGARS_FLAG_FWD_TILE; csrc/render_forward_tc_kernels.cuh): operand tiles in the
     canonical K-major layout, asynchronous MMAs committed to mbarriers (executed by the shim as late as the model allows), TMEM
     accumulators read back with tcgen05.ld."""
-    if emu.variant == "packed":
-        pytest.skip("the build variant only touches the warp-per-block kernels")
+    if emu.variant != "default":
+        pytest.skip("the build variant only touches the warp-per-block forward kernel")
     name, P, H, W, sigma = case
     K = 32
     sc = synthetic.scene(P, H, W, K, sigma_px=sigma)
@@ -136,8 +138,8 @@ def test_backward_kernels(emu, case, kind):
     SAGARS_FLAG_NO_TENSOR_CORES -- csrc/render_backward_kernels.cuh; mma.sync behind SAGARS_FLAG_BWD_TILE --
     csrc/render_backward_mma_kernels.cuh)."""
     name, P, H, W, K, depth, sigma, with_bg = case
-    if emu.variant == "packed" and kind != "warp":
-        pytest.skip("the build variant only touches the warp-per-block kernels")
+    if emu.variant != "default":
+        pytest.skip("the build variant only touches the warp-per-block forward kernel")
     sc = synthetic.scene(P, H, W, K, sigma_px=sigma)
     if name == "k32_opaque":
         sc.gauss.opacities = torch.full_like(sc.gauss.opacities, 0.9995)
