@@ -25,16 +25,29 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # (a candidate's list position rides in the unused 8th float of its record in the warp kernels' candidate tables: measured on
 # B200 in round 2, forward 1.009 -> 0.931 ms at c2, and made the only code path)
-# "fw_bulk": the forward warp kernel with its feature rows fetched by bulk copies on an mbarrier (-DSAGARS_FW_BULK=1, the TMA-unit
-# variant measured against the cp.async default in round 2)
-@pytest.fixture(scope="module", params=["default", "fw_bulk"])
-def emu(request):
+def _build_emu(extra):
     d = tempfile.mkdtemp(prefix="sagars_emu_")
     so = os.path.join(d, "libemu_warp.so")
-    extra = ["-DSAGARS_FW_BULK=1"] if request.param == "fw_bulk" else []
     subprocess.check_call(["g++", "-O1", "-std=c++20", "-pthread", "-ffp-contract=off", "-shared", "-fPIC"] + extra +
                           ["-I", os.path.join(ROOT, "tests", "cuda_emu"), "-I", os.path.join(ROOT, "seganygaussians_b200", "csrc"),
                            os.path.join(ROOT, "tests", "cuda_emu", "emu_warp_kernels.cpp"), "-o", so])
+    return so
+
+
+@pytest.fixture(scope="module")
+def emu_bulk():
+    """The forward warp kernel with its feature rows fetched by bulk copies on an mbarrier (-DSAGARS_FW_BULK=1: the TMA-unit variant
+    measured against the cp.async default in round 2, profiles/r2_render_kernels.md)."""
+    L = C.CDLL(_build_emu(["-DSAGARS_FW_BULK=1"]))
+    L.emu_forward_warp.restype = C.c_int
+    L.emu_forward_warp.argtypes = [C.c_int] * 3 + [C.c_void_p] * 8
+    L.emu_make_geo.argtypes = [C.c_int] + [C.c_void_p] * 3
+    return L
+
+
+@pytest.fixture(scope="module", params=["default"])
+def emu(request):
+    so = _build_emu([])
     L = C.CDLL(so)
     L.variant = request.param
     L.emu_forward_warp.restype = C.c_int
@@ -82,6 +95,16 @@ def _inputs(emu, fw, sc, K):
                                   ("k16", 300, 32, 32, 16, 5.0),
                                   ("k3_warp_any", 300, 32, 32, 3, 5.0)], ids=lambda c: c[0])
 def test_forward_warp_kernel(emu, case):
+    _forward_warp_case(emu, case)
+
+
+@pytest.mark.parametrize("case", [("k32", 260, 32, 32, 32, 5.0), ("k32_ragged", 200, 27, 41, 32, 4.0), ("k32_opaque", 260, 32, 32, 32, 5.0)],
+                         ids=lambda c: c[0])
+def test_forward_warp_kernel_bulk_copy_variant(emu_bulk, case):
+    _forward_warp_case(emu_bulk, case)
+
+
+def _forward_warp_case(emu, case):
     name, P, H, W, K, sigma = case
     sc = synthetic.scene(P, H, W, K, sigma_px=sigma)
     if name == "k32_opaque":
