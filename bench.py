@@ -433,7 +433,7 @@ def main():
         achieved = per_stage_bytes[dom_name] / (dom_avg_ms * 1e-3) / 1e9
         traffic = inst = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and a.workload == "c2":      # the committed capture is of the c2 workload
             try:
                 prof = json.load(open(tp))
                 traffic = prof.get(dom_name)
