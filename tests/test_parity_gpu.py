@@ -215,6 +215,33 @@ def test_cov3d_precomp_path_matches_scale_rotation_path():
     assert float((a - b).abs().max()) < 5e-3 and float((a - b).abs().mean()) < 1e-5
 
 
+def test_mark_visible_matches_the_oracle_and_the_reference():
+    """a2 / a18: `markVisible` point by point -- a cloud that straddles the camera's near plane (view z > 0.2), against the CPU
+    oracle (oracle/sagars_oracle.c, `in_frustum`) and against the unmodified reference's own `GaussianRasterizer.markVisible`."""
+    from seganygaussians_b200 import rasterizer as R
+    from oracle import oracle as orc
+    dev = torch.device("cuda", 0)
+    sc = synthetic.scene(64, 40, 56, 32)
+    c = sc.cam
+    g = torch.Generator().manual_seed(11)
+    pts = c.camera_center[None] + (torch.rand(20000, 3, generator=g) - 0.5) * 8.0          # all around the camera
+    pts = torch.cat([pts, sc.gauss.means3D, (c.camera_center[None] * 3.0).repeat(7, 1)]).contiguous()
+    rs = R.GaussianRasterizationSettings(40, 56, c.tanfovx, c.tanfovy, torch.zeros(32, device=dev), 1.0, c.world_view_transform.to(dev),
+                                         c.full_proj_transform.to(dev), 0, c.camera_center.to(dev), False, False)
+    ours = R.GaussianRasterizerContrastiveF(rs).markVisible(pts.to(dev))
+    assert ours.dtype == torch.bool and ours.shape == (pts.shape[0],)
+    want = orc.mark_visible(pts.numpy(), c.world_view_transform.numpy())
+    assert 0.2 < want.mean() < 0.8                                                           # the cloud really straddles the plane
+    assert np.array_equal(ours.cpu().numpy(), want)
+    if common.have_ref("cf"):
+        ref = common.ref_module("cf")
+        rs_ref = ref.GaussianRasterizationSettings(40, 56, c.tanfovx, c.tanfovy, torch.zeros(32, device=dev), 1.0,
+                                                   c.world_view_transform.to(dev), c.full_proj_transform.to(dev), 0,
+                                                   c.camera_center.to(dev), False, False)
+        theirs = ref.GaussianRasterizer(rs_ref).markVisible(pts.to(dev))
+        assert torch.equal(ours, theirs.to(torch.bool))
+
+
 def test_edge_cases():
     from seganygaussians_b200 import rasterizer as R
     dev = torch.device("cuda", 0)
