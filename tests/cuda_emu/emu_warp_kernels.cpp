@@ -30,10 +30,10 @@ extern "C" int emu_forward_warp(int W, int H, int K, const uint2* ranges, const 
     const int nq = (K + 3) / 4;
 #define GO(NQ_, VEC_) cuda_emu::launch2d(2 * tx, 4 * ty, 32, sizeof(FwSmem<NQ_>), render_forward_warp_kernel<NQ_, VEC_>, ranges, point_list, \
                                          W, H, K, geo, features, bg, final_T, n_contrib, out_color)
-    if (nq <= 1 && !vec) { GO(1, false); return 0; }
-    if (nq <= 2 && !vec) { GO(2, false); return 0; }
-    if (nq <= 4 && vec) { GO(4, true); return 0; }
-    if (nq <= 8 && vec) { GO(8, true); return 0; }
+    // the launcher's dispatch (render_forward_warp.cu): smallest NQ that holds the channels, float4 or scalar feature loads
+#define CASE(NQ_) if (nq <= NQ_) { if (vec) { GO(NQ_, true); } else { GO(NQ_, false); } return 0; }
+    CASE(1) CASE(2) CASE(4) CASE(8) CASE(16)
+#undef CASE
 #undef GO
     return -1;
 }
@@ -47,11 +47,10 @@ extern "C" int emu_backward_warp(int md, int W, int H, int K, const uint2* range
     const int nq = (K + (md ? 1 : 0) + 3) / 4;
 #define GO(NQ_, VEC_, MD_) cuda_emu::launch2d(2 * tx, 4 * ty, 32, sizeof(BwSmem<NQ_>), render_backward_warp_kernel<NQ_, VEC_, MD_, true>, ranges, \
                                               point_list, W, H, K, bg, geo, features, final_T, n_contrib, dL_dpix, dL_dout_mask, ggrad, dL_dcolors)
-    if (md) { if (nq <= 1) { GO(1, false, true); return 0; } return -1; }
-    if (nq <= 1 && !vec) { GO(1, false, false); return 0; }
-    if (nq <= 2 && !vec) { GO(2, false, false); return 0; }
-    if (nq <= 4 && vec) { GO(4, true, false); return 0; }
-    if (nq <= 8 && vec) { GO(8, true, false); return 0; }
+    // the launcher's dispatch (render_backward_warp.cu): smallest NQ that holds the channels, MD / VEC / scalar instance of it
+#define CASE(NQ_) if (nq <= NQ_) { if (md) { GO(NQ_, false, true); } else if (vec) { GO(NQ_, true, false); } else { GO(NQ_, false, false); } return 0; }
+    CASE(1) CASE(2) CASE(4) CASE(8) CASE(16)
+#undef CASE
 #undef GO
     return -1;
 }

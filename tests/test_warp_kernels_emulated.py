@@ -92,7 +92,8 @@ def _inputs(emu, fw, sc, K):
 
 
 @pytest.mark.parametrize("case", [("k32", 260, 32, 32, 32, 5.0), ("k32_ragged", 200, 27, 41, 32, 4.0), ("k32_opaque", 260, 32, 32, 32, 5.0),
-                                  ("k16", 300, 32, 32, 16, 5.0),
+                                  ("k16", 300, 32, 32, 16, 5.0), ("k64", 200, 24, 32, 64, 4.0), ("k12", 260, 32, 32, 12, 5.0),
+                                  ("k5", 260, 32, 32, 5, 5.0),
                                   ("k3_warp_any", 300, 32, 32, 3, 5.0)], ids=lambda c: c[0])
 def test_forward_warp_kernel(emu, case):
     _forward_warp_case(emu, case)
@@ -157,6 +158,21 @@ def test_forward_tcgen05_tile_kernel(emu, case):
                          ids=lambda c: c[0])
 @pytest.mark.parametrize("kind", ["warp", "simt_tile", "mma_tile", "tcgen05"])
 def test_backward_kernels(emu, case, kind):
+    _backward_case(emu, case, kind)
+
+
+@pytest.mark.parametrize("case", [("k64", 160, 24, 32, 64, False, 4.0, True),       # two 32-channel blocks of the S product, 4 m-tiles
+                                  ("k16", 200, 32, 32, 16, False, 5.0, False),      # ROW = 16
+                                  ("k5", 200, 32, 32, 5, False, 5.0, True),         # K % 4 != 0: scalar feature loads, bounds-checked emits
+                                  ("k32_mask", 160, 24, 32, 32, True, 4.0, True)],  # mask gradient as channel K: ROW = 64 with K = 32
+                         ids=lambda c: c[0])
+def test_backward_warp_kernel_other_channel_counts(emu, case):
+    """The default backward at the other template instances (gradient / feature tiles in fragment order for ROW = 8, 16, 64, the
+    channel-block loop, the generic reduction path)."""
+    _backward_case(emu, case, "warp")
+
+
+def _backward_case(emu, case, kind):
     """kind: the default warp-per-block kernel, and the two CTA-per-tile alternates (fp32 SIMT behind
     SAGARS_FLAG_NO_TENSOR_CORES -- csrc/render_backward_kernels.cuh; mma.sync behind SAGARS_FLAG_BWD_TILE --
     csrc/render_backward_mma_kernels.cuh)."""
