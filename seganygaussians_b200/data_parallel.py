@@ -49,6 +49,9 @@ class FeatureGradReducer:
                     dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.group)
             grad.record_stream(self.stream)
             self._pending = ("stream", grad.device)
+        elif self.reduce_fn is not None:
+            self.reduce_fn(grad)                   # the caller's own exchange, synchronous on this path
+            self._pending = None
         else:
             self._pending = ("work", dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         return self._pending

@@ -53,8 +53,14 @@ def _worker(rank, world, port, n_cams, out):
     feats = synthetic.make_gaussians(P, K, W).colors.clone().requires_grad_(True)
     cams = list(range(n_cams))
     dLs = [synthetic.make_upstream(K, H, W, seed=10 + i) for i in cams]
+    calls = []
+    if n_cams == 4:      # one of the two cases goes through a caller-supplied exchange (what bench.py does with the multicast all-reduce)
+        reducer = FeatureGradReducer(side_stream=False, reduce_fn=lambda g: (calls.append(tuple(g.shape)), dist.all_reduce(g))[1])
+    else:
+        reducer = FeatureGradReducer(side_stream=False)
     loss, mine = render_camera_batch(cams, lambda cam, f: _OracleRender.apply(f, (P, H, W, K, cam)), feats,
-                                     lambda img, ci: (img * dLs[ci]).sum(), reducer=FeatureGradReducer(side_stream=False))
+                                     lambda img, ci: (img * dLs[ci]).sum(), reducer=reducer)
+    assert calls == ([(P, K)] if n_cams == 4 else [])
     out[rank] = (feats.grad.clone(), mine, loss)
     dist.barrier()
     dist.destroy_process_group()
