@@ -7,6 +7,9 @@
 //     AND the transaction count reach zero; complete_tx may run ahead of expect_tx (the count goes negative meanwhile).
 // A consumer that reads staged data before the matching wait therefore reads stale bytes, and a byte count or phase-parity
 // mistake ends in the 20-second timeout below instead of a silent pass.
+// -DSAGARS_EMU_ASYNC_EAGER flips to the other extreme: every copy lands the moment it is issued (the transaction count of a bulk
+// copy drops at once too).  A kernel that refills a buffer its threads are still reading -- a write-after-read hazard the "late"
+// mode cannot see -- then computes on the wrong data.  The suites run the staged kernels under both extremes.
 #pragma once
 #include <chrono>
 #include <cstdio>
@@ -66,8 +69,13 @@ inline void check_complete(MBar& b)
 
 }  // namespace emu_async
 
+#if defined(SAGARS_EMU_ASYNC_EAGER)
+inline void cp_async16(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 16); }
+inline void cp_async4(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 4); }
+#else
 inline void cp_async16(void* smem_dst, const void* gmem_src) { emu_async::open_group.push_back({smem_dst, gmem_src}); }
 inline void cp_async4(void* smem_dst, const void* gmem_src) { emu_async::open_group.push_back({smem_dst, gmem_src, 4}); }
+#endif
 inline void cp_async_commit()
 {
     emu_async::groups.push_back(std::move(emu_async::open_group));
@@ -100,7 +108,14 @@ inline void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, 
         std::abort();
     }
     std::lock_guard<std::mutex> lk(emu_async::mu);
+#if defined(SAGARS_EMU_ASYNC_EAGER)
+    emu_async::MBar& b = emu_async::bars.at(bar);
+    std::memcpy(smem_dst, gmem_src, bytes);
+    b.tx -= bytes;                                         // may run ahead of expect_tx, as the model allows
+    emu_async::check_complete(b);
+#else
     emu_async::bars.at(bar).in_flight.push_back({smem_dst, gmem_src, bytes});
+#endif
 }
 inline void mbarrier_wait_parity(uint64_t* bar, uint32_t parity)
 {

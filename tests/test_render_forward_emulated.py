@@ -23,11 +23,14 @@ from seganygaussians_b200 import synthetic
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def emu():
+# "late": asynchronous copies land as late as the programming model allows (a missing wait reads stale bytes); "eager": the moment
+# they are issued (a buffer refilled while it is still being read computes on the wrong data)
+@pytest.fixture(scope="module", params=["late", "eager"])
+def emu(request):
     d = tempfile.mkdtemp(prefix="sagars_emu_")
     so = os.path.join(d, "libemu_render_forward.so")
-    subprocess.check_call(["g++", "-O1", "-std=c++20", "-pthread", "-ffp-contract=off", "-shared", "-fPIC",
+    subprocess.check_call(["g++", "-O1", "-std=c++20", "-pthread", "-ffp-contract=off", "-shared", "-fPIC"] +
+                          (["-DSAGARS_EMU_ASYNC_EAGER"] if request.param == "eager" else []) + [
                            "-I", os.path.join(ROOT, "tests", "cuda_emu"), "-I", os.path.join(ROOT, "seganygaussians_b200", "csrc"),
                            os.path.join(ROOT, "tests", "cuda_emu", "emu_render_forward.cpp"), "-o", so])
     L = C.CDLL(so)
