@@ -28,7 +28,8 @@ def _emulated_kernels_under_asan():
     python -m pytest tests -m "not gpu" -k emulated   -- every kernel that the CPU execution shim (tests/cuda_emu) runs is built with
     AddressSanitizer: an out-of-bounds access to a global array or to the block's shared-memory buffer aborts the run with the
     kernel's source line (the CPU-side counterpart of `compute-sanitizer --tool memcheck`, profiles/r2_sanitizer.md)."""
-    if os.environ.get("SAGARS_EMU_ASAN") != "1":
+    san = "address" if os.environ.get("SAGARS_EMU_ASAN") == "1" else ("thread" if os.environ.get("SAGARS_EMU_TSAN") == "1" else None)
+    if san is None:
         yield
         return
     import subprocess
@@ -36,7 +37,7 @@ def _emulated_kernels_under_asan():
 
     def check_call(cmd, *a, **kw):
         if isinstance(cmd, (list, tuple)) and cmd and cmd[0] == "g++" and "-shared" in cmd and any("cuda_emu" in str(c) for c in cmd):
-            cmd = [cmd[0], "-fsanitize=address", "-fno-omit-frame-pointer", "-g"] + list(cmd[1:])
+            cmd = [cmd[0], "-fsanitize=" + san, "-fno-omit-frame-pointer", "-g"] + list(cmd[1:])
         return orig(cmd, *a, **kw)
 
     subprocess.check_call = check_call

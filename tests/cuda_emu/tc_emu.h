@@ -167,7 +167,9 @@ inline void mbar_wait_long(uint64_t* bar, uint32_t parity, uint32_t = 0) { mbar_
 inline void fence_smem_to_async_proxy() {}
 inline void fence_before_sync() {}
 inline void fence_after_sync() {}
-template <int NCOLS> inline void tmem_alloc(uint32_t* slot) { *slot = 0u; }
+// warp-collective on the device (one write); here every lane of the warp stores the same value -- atomically, so that a
+// ThreadSanitizer build of the suite (tests/conftest.py, SAGARS_EMU_TSAN) reports the kernels' races, not the shim's
+template <int NCOLS> inline void tmem_alloc(uint32_t* slot) { __atomic_store_n(slot, 0u, __ATOMIC_RELAXED); }
 template <int NCOLS> inline void tmem_dealloc(uint32_t) {}
 inline void tmem_ld32(uint32_t taddr, float* v)
 {
